@@ -1,0 +1,47 @@
+"""Load the UNMODIFIED reference module when /root/reference is present.  TEST INFRASTRUCTURE ONLY.
+
+The reference's forward calls `.cuda()` on a freshly built ones-weight
+(/root/reference/cspn_pytorch/models/cspn.py:50), so it cannot run on a CPU-only
+host as is.  `load_reference()` imports the file by path and, only while a reference
+forward runs on CPU tensors, makes `Tensor.cuda` the identity.  Nothing is copied.
+
+/root/reference does not exist on the GPU box: callers must check `available()`.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import os
+
+REF_FILE = '/root/reference/cspn_pytorch/models/cspn.py'
+
+
+def available() -> bool:
+    return os.path.isfile(REF_FILE)
+
+
+def load_reference():
+    spec = importlib.util.spec_from_file_location('_reference_cspn', REF_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@contextlib.contextmanager
+def cuda_identity_shim():
+    import torch
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
+
+
+def reference_forward(guidance, blur_depth, sparse_depth, prop_time, norm_type):
+    """Run reference Affinity_Propagate on CPU torch tensors; returns a torch tensor."""
+    import torch
+    mod = load_reference()
+    layer = mod.Affinity_Propagate(prop_time, 3, norm_type)
+    with torch.no_grad(), cuda_identity_shim():
+        return layer(guidance, blur_depth, sparse_depth)
