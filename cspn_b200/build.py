@@ -1,0 +1,91 @@
+"""Build libcspn_b200.so (the C-ABI product library) in-tree with nvcc for sm_100a.
+
+    python -m cspn_b200.build [--force]
+
+Output: cspn_b200/_build/libcspn_b200.so (git-ignored; travels to the GPU box with gpurun).
+No torch headers are involved: the library is plain CUDA C++ behind include/cspn_b200.h.
+"""
+import glob
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OUT_DIR = os.path.join(HERE, '_build')
+LIB = os.path.join(OUT_DIR, 'libcspn_b200.so')
+STAMP = os.path.join(OUT_DIR, 'sources.sha256')
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a',
+    '-O3', '-std=c++17', '-lineinfo',
+    '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
+    '--expt-relaxed-constexpr',
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def _sources():
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for f in _sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + \
+            [os.path.join(os.path.dirname(HERE), 'include', 'cspn_b200.h')]:
+        h.update(f.encode())
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def up_to_date():
+    return (os.path.isfile(LIB) and os.path.isfile(STAMP)
+            and open(STAMP).read().strip() == _digest())
+
+
+def build(force=False, verbose=False):
+    """Compiles every .cu under csrc/ (separately, in parallel) and links the shared library."""
+    if not force and up_to_date():
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    env = dict(os.environ)
+    # the image exports CC=/opt/gcc/bin/gcc; nvcc wants the system g++ as host compiler
+    ccbin = ['-ccbin', '/usr/bin/g++'] if os.path.isfile('/usr/bin/g++') else []
+    procs = []
+    objs = []
+    for src in _sources():
+        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + ['-Xptxas', '-v', '-c', src, '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f'== {os.path.basename(src)}\n{out}')
+        if p.returncode != 0:
+            sys.stderr.write('\n'.join(log))
+            raise RuntimeError(f'nvcc failed on {src}')
+    with open(os.path.join(OUT_DIR, 'ptxas.log'), 'w') as fh:
+        fh.write('\n'.join(log))
+    if verbose:
+        print('\n'.join(log))
+    link = [nvcc] + ccbin + ['-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs
+    subprocess.check_call(link, env=env)
+    with open(STAMP, 'w') as fh:
+        fh.write(_digest())
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

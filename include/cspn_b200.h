@@ -1,0 +1,125 @@
+/* cspn_b200 -- C ABI of the B200-native CSPN propagation path.
+ *
+ * The reference (XinJCheng/CSPN) has no FFI: its hot path is a Python nn.Module,
+ *   Affinity_Propagate.forward(guidance, blur_depth, sparse_depth=None)
+ *     /root/reference/cspn_pytorch/models/cspn.py:42-83        (2D, 8 neighbours)
+ *   fluid.layers.affinity_propagate(feat, gate_weight, kernel_size=3) iterated prop_step times
+ *     /root/reference/cspn_paddle/demo.py:20-54                 (3D, 26 neighbours; op source not in tree)
+ * Each entry point below is what a binding for those two call sites would bind
+ * (INTEGRATION.md shows the ctypes stub and the drop-in `cspn.py`).
+ *
+ * Conventions
+ *   - all tensors fp32, row-major NCHW / NCDHW, W fastest, dense (contiguous) planes;
+ *   - *_f32 entry points take DEVICE pointers and enqueue on `stream` without synchronising
+ *     or allocating; the caller provides `workspace` (size from *_workspace_bytes; may be
+ *     NULL when that returns 0);
+ *   - *_f32_host entry points take HOST pointers (pinned for full speed, pageable works),
+ *     copy H2D / run / copy D2H in a chunked 3-stage pipeline and block until `out` is valid;
+ *   - return value: CSPN_OK (0) or a negative cspn_status; cspn_last_error() gives the text
+ *     (thread-local);
+ *   - re-entrant and thread-safe: per-call state only, the tensor-map/launch-config cache is
+ *     mutex-protected; one process per GPU is the intended deployment (torchrun), but
+ *     DataParallel-style threads (reference eval.py:117) are safe too: the device of
+ *     `blur`/`feat` is made current for the call and restored afterwards.
+ */
+#ifndef CSPN_B200_H_
+#define CSPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* cspn_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define CSPN_API __attribute__((visibility("default")))
+#else
+#define CSPN_API
+#endif
+
+typedef enum {
+    CSPN_OK = 0,
+    CSPN_ERR_INVALID_ARGUMENT = -1, /* bad shape / null pointer / unknown enum (reference: AssertionError, cspn.py:33,36) */
+    CSPN_ERR_WORKSPACE = -2,        /* workspace missing or too small */
+    CSPN_ERR_CUDA = -3,             /* a CUDA call failed; text in cspn_last_error() */
+    CSPN_ERR_UNSUPPORTED = -4       /* requested algorithm cannot run this shape */
+} cspn_status;
+
+/* norm_type of Affinity_Propagate.__init__ (cspn.py:16-36) */
+typedef enum {
+    CSPN_NORM_8SUM = 0,     /* '8sum'     */
+    CSPN_NORM_8SUM_ABS = 1  /* '8sum_abs' */
+} cspn_norm2d;
+
+/* 3D normalisation */
+typedef enum {
+    CSPN_NORM_26SUM = 0,     /* gathered affinities, signed, centre term (cspn.py scheme in 3D)          */
+    CSPN_NORM_26SUM_ABS = 1, /* same with |g|                                                           */
+    CSPN_NORM_PADDLE = 2     /* |g| normalised at the voxel's own location, no centre term (demo.py:24,47-52) */
+} cspn_norm3d;
+
+typedef enum {
+    CSPN_ALGO_AUTO = 0,    /* cluster kernel when the shape allows, else generic                         */
+    CSPN_ALGO_GENERIC = 1, /* prep kernel + one stencil launch per iteration (any shape; needs workspace) */
+    CSPN_ALGO_CLUSTER = 2  /* single launch: TMA-staged tiles, register-resident state for all iterations,
+                              DSMEM halo exchange inside a thread-block cluster                          */
+} cspn_algo;
+
+/* ---- 2D: replaces Affinity_Propagate.forward (cspn.py:42-83) --------------------------------
+ * guidance [B][guidance_channels>=8][H][W] (channels 0..7 used, cspn.py:91-98)
+ * blur     [B][C][H][W]   (C>1: affinity shared across channels, cspn.py:70 via Conv3d)
+ * sparse   [B][1][H][W] or NULL (only its sign is used, cspn.py:63-64)
+ * out      [B][C][H][W]   must not alias the inputs
+ * iters    prop_time >= 0 (0 copies blur to out, cspn.py:61,83)
+ */
+CSPN_API size_t cspn2d_workspace_bytes(int B, int C, int H, int W, int iters, int algo);
+
+CSPN_API int cspn2d_fwd_f32(const float* guidance, const float* blur, const float* sparse, float* out,
+                   int B, int C, int H, int W, int guidance_channels, int iters, int norm_type,
+                   int algo, void* workspace, size_t workspace_bytes, cspn_stream_t stream);
+
+CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* blur, const float* sparse, float* out,
+                        int B, int C, int H, int W, int guidance_channels, int iters, int norm_type,
+                        int algo, int device);
+
+/* ---- 2D backward (adjoint of the above; reference: autograd through cspn.py:42-83, used by
+ * train.py:198).  grad_guidance [B][guidance_channels][H][W] (channels >= 8 are zero-filled),
+ * grad_blur [B][C][H][W].  Either may be NULL.  Needs the forward inputs again. */
+CSPN_API size_t cspn2d_bwd_workspace_bytes(int B, int C, int H, int W, int iters);
+
+CSPN_API int cspn2d_bwd_f32(const float* guidance, const float* blur, const float* sparse, const float* grad_out,
+                   float* grad_guidance, float* grad_blur,
+                   int B, int C, int H, int W, int guidance_channels, int iters, int norm_type,
+                   void* workspace, size_t workspace_bytes, cspn_stream_t stream);
+
+/* ---- 3D: replaces CSPN.cspn(guide, feat) (cspn_paddle/demo.py:20-54) ------------------------
+ * guidance [B][26][D][H][W], feat/out [B][C][D][H][W] (gate shared across C, cspn_paddle/README.md:56)
+ */
+CSPN_API size_t cspn3d_workspace_bytes(int B, int C, int D, int H, int W, int iters);
+
+CSPN_API int cspn3d_fwd_f32(const float* guidance, const float* feat, float* out,
+                   int B, int C, int D, int H, int W, int iters, int norm_type,
+                   void* workspace, size_t workspace_bytes, cspn_stream_t stream);
+
+CSPN_API int cspn3d_fwd_f32_host(const float* guidance, const float* feat, float* out,
+                        int B, int C, int D, int H, int W, int iters, int norm_type, int device);
+
+/* ---- pinned host buffers for the *_host entry points ---------------------------------------- */
+CSPN_API void* cspn_host_alloc(size_t bytes); /* cudaHostAlloc; NULL on failure */
+CSPN_API void cspn_host_free(void* p);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+CSPN_API const char* cspn_last_error(void);   /* thread-local, never NULL */
+CSPN_API int cspn_version(void);              /* 10000*major + 100*minor + patch */
+CSPN_API int cspn_last_algo(void);            /* cspn_algo actually used by this thread's last 2D forward */
+CSPN_API int cspn_last_launches(void);        /* kernels this thread's last call launched */
+/* Human-readable plan for a 2D shape (tile geometry, cluster size, strips); returns bytes written. */
+CSPN_API int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int algo, char* buf, int buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPN_B200_H_ */

@@ -1,0 +1,49 @@
+"""GPU parity of the 3D path against the (reference-unpinned) oracle, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import cspn_b200
+from cspn_b200.synth import make_inputs_3d
+from oracle import c_oracle, cspn_numpy as onp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('mode', ['26sum', '26sum_abs', 'paddle'])
+@pytest.mark.parametrize('shape,n', [((2, 1, 6, 10, 12), 4), ((1, 2, 16, 24, 40), 12), ((1, 1, 1, 9, 11), 3),
+                                      ((1, 1, 5, 1, 1), 2)])
+def test_3d_against_oracle(shape, n, mode):
+    B, C, D, H, W = shape
+    g, f = make_inputs_3d(5, B, C, D, H, W, signed=(mode == '26sum'))
+    ref = c_oracle.cspn3d(g.numpy(), f.numpy(), n, mode)
+    out = cspn_b200.Affinity_Propagate3D(n, 3, mode)(g.cuda(), f.cuda()).cpu().numpy()
+    ok, ratio, normwise = onp.parity_ok(out, ref, 1e-4)
+    assert ok, (ratio, normwise)
+
+
+def test_3d_full_size_properties():
+    """BASELINE cfg4 shape (8,1,64,96,312), N=12: linearity, constant preservation, one slab vs the oracle."""
+    B, C, D, H, W = 2, 1, 64, 96, 312          # two of the eight volumes: volumes are independent
+    g, f = [t.cuda() for t in make_inputs_3d(6, B, C, D, H, W)]
+    m = cspn_b200.Affinity_Propagate3D(12, 3, '26sum_abs')
+    out = m(g, f)
+    assert torch.isfinite(out).all()
+    f2 = torch.rand_like(f)
+    lhs = m(g, 0.5 * f + 3 * f2)
+    rhs = 0.5 * out + 3 * m(g, f2)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-4)
+    const = torch.full_like(f, 1.25)
+    assert torch.allclose(m(g, const), const, rtol=1e-5)
+    assert torch.allclose(cspn_b200.Affinity_Propagate3D(12, 3, 'paddle')(g, const)[:, :, 12:-12, 12:-12, 12:-12],
+                          const[:, :, 12:-12, 12:-12, 12:-12], rtol=1e-5)
+    ref = c_oracle.cspn3d(g[:1].cpu().numpy(), f[:1].cpu().numpy(), 12, '26sum_abs')
+    ok, ratio, normwise = onp.parity_ok(out[:1].cpu().numpy(), ref, 1e-4)
+    assert ok, (ratio, normwise)
+
+
+def test_3d_host_entry_point():
+    g, f = make_inputs_3d(8, 3, 1, 8, 12, 16)
+    a = cspn_b200.propagate3d(g, f, 5, 'paddle')
+    b = cspn_b200.propagate3d(g.cuda(), f.cuda(), 5, 'paddle').cpu()
+    assert torch.equal(a, b)
