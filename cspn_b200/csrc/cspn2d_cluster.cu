@@ -1,14 +1,647 @@
-// Cluster kernel (single launch, register-resident state, DSMEM halo exchange) -- placeholder
-// until the kernel lands; AUTO falls back to the generic path.
+// 2D CSPN, all N iterations in ONE launch with HBM touched once per tile (sm_100a).
+//
+// Reference arithmetic: /root/reference/cspn_pytorch/models/cspn.py:42-144 (see cspn2d_generic.cu
+// for the folded form d <- c' + sum_k w'_k shift_k(d)).
+//
+// Decomposition
+//   task     = (image b, channel c, x-strip j).  A strip is TW = 32*PC columns wide; when the image is
+//              wider than one strip, neighbouring strips overlap by a halo of N columns per side (the
+//              stale region creeps inwards one column per iteration, so after N iterations the strip's
+//              "useful" columns are still exact).  Rows are never tiled: zero padding at the top/bottom of
+//              the image is the reference's own boundary condition, so a task always spans the full height.
+//   cluster  = one task.  The CS CTAs of a thread-block cluster stack along y; CTA r owns the band of
+//              RB = NW*PR rows starting at r*RB.  (CS*RB >= H.)
+//   CTA      = NW warps stacked along y; warp wy owns PR rows; lane l owns PC consecutive columns.
+//   thread   = a PR x PC pixel patch whose ENTIRE state lives in registers for all N iterations:
+//              8 folded weights + the constant term + the current value per pixel (10 registers/pixel).
+// Data movement
+//   * the 8 guidance planes arrive by TMA (cp.async.bulk.tensor.3d), one box per channel whose origin is
+//     shifted by that channel's (dy,dx): the box lands in shared memory as the GATHERED affinity a_k
+//     (cspn.py:105-132), and TMA's out-of-bounds zero fill is exactly ZeroPad2d;
+//   * blur depth / sparse depth are read once with vectorised global loads, the result is written once;
+//   * per iteration, x-neighbours come from warp shuffles, y-neighbours inside a thread from its own
+//     registers, across warps from a double-buffered shared-memory row exchange, and across CTAs of the
+//     cluster from the same exchange buffers written remotely through DSMEM with st.async, whose
+//     complete_tx lands on the consumer's mbarrier: pure dataflow, one mbarrier wait per iteration and no
+//     cluster-wide barrier inside the loop.  Boundary rows of each patch are computed and published first,
+//     so the DSMEM latency hides behind the interior rows.
+// No tensor cores: a 9-point stencil with per-pixel weights is FMA + HBM bound, not a contraction.
+#include <cooperative_groups.h>
+
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
+
 namespace cspn {
-bool cluster2d_supported(const Problem2D&, char* why, int why_len) {
-    snprintf(why, why_len, "cluster kernel not built yet");
-    return false;
+
+namespace {
+
+constexpr int kMaxStrips = 40;
+
+struct ClusterParams {
+    const float* blur;    // [B*C][H][W]
+    const float* sparse;  // [B][H][W] or null
+    float* out;           // [B*C][H][W]
+    int C, H, W, gch, iters, norm_abs;
+    int n_strips;
+    int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
+    int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
+    int ux1[kMaxStrips];
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int cluster2d_forward(const Problem2D&, cudaStream_t, int*) {
-    set_error("cluster kernel not built yet");
-    return CSPN_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-int cluster2d_describe(int, int, int, int, int, char* buf, int len) { return snprintf(buf, len, "cluster: n/a"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// remote store whose completion is signalled on the REMOTE mbarrier (complete_tx of the bytes stored)
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     remote_addr),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, float2 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+                 "f"(v.x), "f"(v.y), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------
+// Shared memory map (dynamic):
+//   [0, 8*RB*TW*4)            stage: 8 gathered-affinity planes [k][RB][TW]   (TMA destination, 128 B aligned)
+//   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
+//   then 3 mbarriers          tma, full[0], full[1]
+template <int PR, int PC, int NW>
+struct Cfg {
+    static constexpr int kThreads = 32 * NW;
+    static constexpr int RB = NW * PR;   // rows per CTA band
+    static constexpr int TW = 32 * PC;   // tile (strip) width
+    static constexpr int kSlots = 2 * NW + 2;
+    static constexpr size_t kStageBytes = (size_t)8 * RB * TW * sizeof(float);
+    static constexpr size_t kXchBytes = (size_t)2 * kSlots * TW * sizeof(float);
+    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + 64;
+    static_assert(PC % 2 == 0 && PC <= 8, "PC must be 2, 4, 6 or 8 (TMA box <= 256 columns)");
+    static_assert(RB <= 256, "TMA box rows");
+};
+
+// Row vector of PC pixels with its two x-neighbours: e[0] = left, e[1..PC] = own, e[PC+1] = right.
+template <int PC>
+__device__ __forceinline__ void extend_row(const float (&v)[PC], float (&e)[PC + 2], int lane) {
+    float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+    float r = __shfl_down_sync(0xffffffffu, v[0], 1);
+    e[0] = (lane == 0) ? 0.f : l;    // outside the tile: treated as 0 (image border, or strip halo that decays)
+    e[PC + 1] = (lane == 31) ? 0.f : r;
+#pragma unroll
+    for (int j = 0; j < PC; ++j) e[j + 1] = v[j];
+}
+
+// new value of one row: c + sum_k w_k * neighbour_k ; up = row y-1, cur = row y, dn = row y+1 (extended rows)
+template <int PC>
+__device__ __forceinline__ void stencil_row(const float (&w)[PC][8], const float (&c)[PC], const float (&up)[PC + 2],
+                                            const float (&cur)[PC + 2], const float (&dn)[PC + 2], float (&o)[PC]) {
+#pragma unroll
+    for (int j = 0; j < PC; ++j) {
+        float acc = c[j];
+        acc = fmaf(w[j][0], dn[j + 2], acc);   // (+1,+1)
+        acc = fmaf(w[j][1], dn[j + 1], acc);   // (+1, 0)
+        acc = fmaf(w[j][2], dn[j], acc);       // (+1,-1)
+        acc = fmaf(w[j][3], cur[j + 2], acc);  // ( 0,+1)
+        acc = fmaf(w[j][4], cur[j], acc);      // ( 0,-1)
+        acc = fmaf(w[j][5], up[j + 2], acc);   // (-1,+1)
+        acc = fmaf(w[j][6], up[j + 1], acc);   // (-1, 0)
+        acc = fmaf(w[j][7], up[j], acc);       // (-1,-1)
+        o[j] = acc;
+    }
+}
+
+template <int PC>
+__device__ __forceinline__ void load_row_smem(const float* p, float (&v)[PC]) {
+    if constexpr (PC % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < PC / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < PC / 2; ++q) {
+            const float2 t = *reinterpret_cast<const float2*>(p + 2 * q);
+            v[2 * q] = t.x; v[2 * q + 1] = t.y;
+        }
+    }
+}
+template <int PC>
+__device__ __forceinline__ void store_row_smem(float* p, const float (&v)[PC]) {
+    if constexpr (PC % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < PC / 4; ++q)
+            *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < PC / 2; ++q) *reinterpret_cast<float2*>(p + 2 * q) = make_float2(v[2 * q], v[2 * q + 1]);
+    }
+}
+template <int PC>
+__device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)[PC], uint32_t bar) {
+    if constexpr (PC % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < PC / 4; ++q)
+            st_async_v4(addr + 16 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), bar);
+    } else {
+#pragma unroll
+        for (int q = 0; q < PC / 2; ++q) st_async_v2(addr + 8 * q, make_float2(v[2 * q], v[2 * q + 1]), bar);
+    }
+}
+
+template <int PR, int PC, int NW>
+__global__ void __launch_bounds__(32 * NW, 1)
+cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
+    using K = Cfg<PR, PC, NW>;
+    constexpr int RB = K::RB, TW = K::TW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes);
+    const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_full1 = smem_u32(bars + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    const int task = (int)cluster_id_x();
+    const int strip = task % prm.n_strips;
+    const int bc = task / prm.n_strips;  // b*C + c
+    const int b = bc / prm.C;
+    const int H = prm.H, W = prm.W;
+    const int tile_x0 = prm.tile_x0[strip];
+    const int band_y0 = (int)crank * RB;
+    const bool has_up = crank > 0, has_dn = crank + 1 < csize;
+
+    // bytes of halo rows this CTA RECEIVES per exchange (one row of TW floats from each existing neighbour)
+    const uint32_t rx_bytes = (uint32_t)((has_up ? 1 : 0) + (has_dn ? 1 : 0)) * TW * sizeof(float);
+
+    if (tid == 0) {
+        mbar_init(bar_tma, 1);
+        mbar_init(bar_full0, NW);
+        mbar_init(bar_full1, NW);
+        fence_barrier_init();
+        fence_proxy_async();
+        // a band that starts below the image has nothing to load (its pixels are all masked out)
+        mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            tma_load_3d(smem_u32(stage + (size_t)k * RB * TW), &tm_guidance, tile_x0 + off2_dx(k), band_y0 + off2_dy(k),
+                        b * prm.gch + k, bar_tma);
+    }
+    // every CTA's barriers must be initialised before a neighbour's st.async can target them
+    cluster_arrive();
+
+    // ---- thread state ---------------------------------------------------------------------------
+    float w[PR][PC][8], c[PR][PC], d[PR][PC];
+    const int x_thr = tile_x0 + lane * PC;  // first column of this thread
+    const int y_thr = band_y0 + wy * PR;    // first row of this thread
+    const size_t HW = (size_t)H * W;
+    const float* blur = prm.blur + (size_t)bc * HW;
+    const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
+
+    // blur / sparse: straight from global (aligned, read once); overlaps with the TMA in flight
+    float m[PR][PC];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+        const int y = y_thr + r;
+#pragma unroll
+        for (int q = 0; q < PC / 2; ++q) {
+            const int x = x_thr + 2 * q;
+            // W % 4 == 0 and x even: a float2 is entirely inside or outside the image
+            const bool in = (y < H) && (x >= 0) && (x < W);
+            float2 dv = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
+            if (in) {
+                dv = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + x));
+                if (sparse) sv = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + x));
+            }
+            d[r][2 * q] = dv.x; d[r][2 * q + 1] = dv.y;
+            m[r][2 * q] = signf(sv.x); m[r][2 * q + 1] = signf(sv.y);
+        }
+    }
+
+    cluster_wait();
+    mbar_wait(bar_tma, 0);
+
+    // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+        const int y = y_thr + r;
+        float a[8][PC];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) load_row_smem<PC>(stage + ((size_t)k * RB + wy * PR + r) * TW + lane * PC, a[k]);
+#pragma unroll
+        for (int j = 0; j < PC; ++j) {
+            const int x = x_thr + j;
+            const bool in = (y < H) && (x >= 0) && (x < W);
+            float S = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (prm.norm_abs) a[k][j] = fabsf(a[k][j]);
+                S += fabsf(a[k][j]);
+            }
+            const float inv = __frcp_rn(S);  // 1/0 = inf, 0*inf = NaN: the reference's 0/0 (cspn.py:138)
+            const float om = 1.f - m[r][j];
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float wk = a[k][j] * inv;
+                s += wk;
+                w[r][j][k] = in ? om * wk : 0.f;
+            }
+            const float kappa = om * (1.f - s) + m[r][j];
+            c[r][j] = in ? kappa * d[r][j] : 0.f;
+        }
+    }
+
+    // ---- exchange-buffer helpers -------------------------------------------------------------------
+    // slot 0: halo row from the CTA above; slots 1+2wy / 2+2wy: top / bottom row of warp wy; last: halo from below
+    auto xrow = [&](int parity, int slot) { return xch + ((size_t)parity * K::kSlots + slot) * TW + lane * PC; };
+    const uint32_t up_rank = crank - 1, dn_rank = crank + 1;
+
+    // publish boundary rows of the current d into buffer `parity` and signal full[parity]
+    auto publish = [&](int parity, const float (&top)[PC], const float (&bot)[PC]) {
+        store_row_smem<PC>(xrow(parity, 1 + 2 * wy), top);
+        store_row_smem<PC>(xrow(parity, 2 + 2 * wy), bot);
+        const uint32_t bar_local = parity ? bar_full1 : bar_full0;
+        if (wy == 0 && has_up)  // my top row is the "halo from below" of the CTA above
+            store_row_remote<PC>(map_to_cta(smem_u32(xrow(parity, K::kSlots - 1)), up_rank), top, map_to_cta(bar_local, up_rank));
+        if (wy == NW - 1 && has_dn)  // my bottom row is the "halo from above" of the CTA below
+            store_row_remote<PC>(map_to_cta(smem_u32(xrow(parity, 0)), dn_rank), bot, map_to_cta(bar_local, dn_rank));
+        __syncwarp();
+        if (lane == 0) {
+            if (wy == 0 && rx_bytes) mbar_arrive_expect_tx(bar_local, rx_bytes);
+            else mbar_arrive(bar_local);
+        }
+    };
+
+    // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
+    if (!has_up) {
+        for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
+    }
+    if (!has_dn) {
+        for (int i = tid; i < TW; i += K::kThreads) {
+            xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
+            xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
+        }
+    }
+    __syncthreads();  // zeroed halo slots visible; everybody is done reading `stage`
+
+    const int iters = prm.iters;
+    if (iters > 0) publish(0, d[0], d[PR - 1]);
+
+    // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
+    for (int it = 0; it < iters; ++it) {
+        const int par = it & 1;
+        mbar_wait(par ? bar_full1 : bar_full0, (uint32_t)((it >> 1) & 1));
+
+        // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
+        float up[PC + 2], dn[PC + 2], e[PR][PC + 2];
+        {
+            float t[PC];
+            load_row_smem<PC>(xrow(par, 2 * wy), t);      // row above my patch
+            extend_row<PC>(t, up, lane);
+            load_row_smem<PC>(xrow(par, 2 * wy + 3), t);  // row below my patch
+            extend_row<PC>(t, dn, lane);
+        }
+#pragma unroll
+        for (int r = 0; r < PR; ++r) extend_row<PC>(d[r], e[r], lane);
+        // boundary rows first: they go out to the neighbours (shared memory / DSMEM) and the latency of that
+        // exchange hides behind the interior rows computed afterwards
+        float new_top[PC], new_bot[PC];
+        if constexpr (PR == 1) {
+            stencil_row<PC>(w[0], c[0], up, e[0], dn, new_top);
+#pragma unroll
+            for (int j = 0; j < PC; ++j) new_bot[j] = new_top[j];
+        } else {
+            stencil_row<PC>(w[0], c[0], up, e[0], e[1], new_top);
+            stencil_row<PC>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, new_bot);
+        }
+        if (it + 1 < iters) publish(par ^ 1, new_top, new_bot);
+#pragma unroll
+        for (int r = 1; r <= PR - 2; ++r) stencil_row<PC>(w[r], c[r], e[r - 1], e[r], e[r + 1], d[r]);
+#pragma unroll
+        for (int j = 0; j < PC; ++j) { d[0][j] = new_top[j]; d[PR - 1][j] = new_bot[j]; }
+    }
+
+    // ---- epilogue: useful columns straight to global ------------------------------------------------
+    float* out = prm.out + (size_t)bc * HW;
+    const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+        const int y = y_thr + r;
+        if (y >= H) continue;
+        if constexpr (PC % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < PC / 4; ++q) {
+                const int x = x_thr + 4 * q;
+                if (x >= ux0 && x < ux1)
+                    __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x),
+                           make_float4(d[r][4 * q], d[r][4 * q + 1], d[r][4 * q + 2], d[r][4 * q + 3]));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PC / 2; ++q) {
+                const int x = x_thr + 2 * q;
+                if (x >= ux0 && x < ux1)
+                    __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + x), make_float2(d[r][2 * q], d[r][2 * q + 1]));
+            }
+        }
+    }
+    // No CTA may exit while a neighbour could still address its shared memory.
+    cluster_arrive();
+    cluster_wait();
+}
+
+// ---- host side: configurations, planner, launch ---------------------------------------------------
+
+struct KernelCfg {
+    int PR, PC, NW;
+    const void* fn;
+    size_t smem;
+    int RB() const { return PR * NW; }
+    int TW() const { return 32 * PC; }
+};
+
+template <int PR, int PC, int NW>
+KernelCfg make_cfg() {
+    return KernelCfg{PR, PC, NW, (const void*)&cspn2d_cluster_kernel<PR, PC, NW>, Cfg<PR, PC, NW>::kSmemBytes};
+}
+
+// The menu the planner picks from.  Register budget: 10 registers per pixel of state; PR*PC <= 20 pixels
+// at 256 threads (255 registers), <= 16 at 288-320 threads.
+const std::vector<KernelCfg>& configs() {
+    static const std::vector<KernelCfg> v = {
+        make_cfg<5, 4, 8>(),   // 40 rows x 128 cols, 256 thr, 20 px/thread
+        make_cfg<4, 4, 8>(),   // 32 x 128
+        make_cfg<3, 6, 8>(),   // 24 x 192
+        make_cfg<2, 8, 8>(),   // 16 x 256
+        make_cfg<2, 4, 8>(),   // 16 x 128 (small images)
+    };
+    return v;
+}
+
+struct Plan {
+    int cfg = -1, cs = 0, n_strips = 0;
+    int tile_x0[kMaxStrips], ux0[kMaxStrips], ux1[kMaxStrips];
+    double cost = 0;
+    int max_clusters = 0;
+};
+
+std::mutex g_mu;
+struct OccKey { int cfg, cs, dev; };
+std::vector<std::pair<OccKey, int>> g_occ_cache;
+bool g_attr_set[16][16] = {};
+
+// how many clusters of `cs` CTAs of configuration `ci` can be co-resident on the device
+int max_active_clusters(int ci, int cs, int dev) {
+    for (auto& e : g_occ_cache)
+        if (e.first.cfg == ci && e.first.cs == cs && e.first.dev == dev) return e.second;
+    const KernelCfg& k = configs()[ci];
+    if (!g_attr_set[dev & 15][ci]) {
+        if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k.fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        g_attr_set[dev & 15][ci] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * 64);
+    cfg.blockDim = dim3(32 * k.NW);
+    cfg.dynamicSmemBytes = k.smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k.fn, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    g_occ_cache.push_back({OccKey{ci, cs, dev}, n});
+    return n;
+}
+
+// Strip layout for tile width TW and halo `halo`; returns false if it does not fit kMaxStrips.
+bool layout_strips(int W, int TW, int halo, Plan& p) {
+    p.n_strips = 0;
+    if (TW >= W) {
+        p.tile_x0[0] = 0; p.ux0[0] = 0; p.ux1[0] = W; p.n_strips = 1;
+        return true;
+    }
+    const int halo4 = (halo + 3) & ~3;
+    if (TW - 2 * halo4 < 16) return false;
+    int u = 0;
+    while (u < W) {
+        if (p.n_strips == kMaxStrips) return false;
+        const int x0 = (u == 0) ? 0 : u - halo4;
+        int u1 = (x0 + TW >= W) ? W : x0 + TW - halo4;
+        p.tile_x0[p.n_strips] = x0; p.ux0[p.n_strips] = u; p.ux1[p.n_strips] = u1;
+        ++p.n_strips;
+        u = u1;
+    }
+    return true;
+}
+
+// Picks (configuration, cluster size, strips) minimising waves x per-task work.  `dev` < 0: no device
+// query (planning on a CPU-only box for describe_plan): assume the B200 occupancy table measured by tools/probe.
+bool make_plan(int B, int C, int H, int W, int iters, int dev, Plan& best, char* why, int why_len) {
+    if (W % 4 != 0) { snprintf(why, why_len, "W=%d is not a multiple of 4 (TMA row pitch / vector stores)", W); return false; }
+    static const int kProbe256[17] = {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7};
+    best.cfg = -1;
+    const auto& cf = configs();
+    for (int ci = 0; ci < (int)cf.size(); ++ci) {
+        const KernelCfg& k = cf[ci];
+        const int cs = (H + k.RB() - 1) / k.RB();
+        if (cs > 16) continue;
+        Plan p;
+        if (!layout_strips(W, k.TW(), iters, p)) continue;
+        const int mac = dev >= 0 ? max_active_clusters(ci, cs, dev) : kProbe256[cs];
+        if (mac <= 0) continue;
+        const long tasks = (long)B * C * p.n_strips;
+        const long waves = (tasks + mac - 1) / mac;
+        // per-task time ~ pixels per CTA x (8 FMA/iter + prologue), issue-bound
+        p.cost = (double)waves * k.RB() * k.TW() * (8.0 * iters + 60.0);
+        p.cfg = ci; p.cs = cs; p.max_clusters = mac;
+        if (best.cfg < 0 || p.cost < best.cost) best = p;
+    }
+    if (best.cfg < 0) {
+        snprintf(why, why_len, "no cluster configuration covers H=%d W=%d iters=%d (H too tall for 16 bands or halo too wide)", H, W, iters);
+        return false;
+    }
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode() {
+    if (g_encode) return CSPN_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CSPN_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return CSPN_ERR_CUDA;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    return CSPN_OK;
+}
+
+}  // namespace
+
+bool cluster2d_supported(const Problem2D& p, char* why, int why_len) {
+    if (p.iters <= 0) { snprintf(why, why_len, "iters == 0"); return false; }
+    if ((reinterpret_cast<uintptr_t>(p.guidance) | reinterpret_cast<uintptr_t>(p.blur) | reinterpret_cast<uintptr_t>(p.sparse) |
+         reinterpret_cast<uintptr_t>(p.out)) & 15) {
+        snprintf(why, why_len, "tensor base pointers must be 16-byte aligned");
+        return false;
+    }
+    if ((long)p.B * p.gch > 2147483647L) { snprintf(why, why_len, "B*gch too large"); return false; }
+    int dev = -1;
+    if (p.blur) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; } }
+    std::lock_guard<std::mutex> lock(g_mu);
+    Plan plan;
+    return make_plan(p.B, p.C, p.H, p.W, p.iters, dev, plan, why, why_len);
+}
+
+int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    Plan plan;
+    char why[200] = "";
+    int dev = -1, ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) cudaGetDevice(&dev); else cudaGetLastError();
+    if (!make_plan(B, C, H, W, iters, dev, plan, why, sizeof(why))) return snprintf(buf, len, "cluster: unsupported (%s)", why);
+    const KernelCfg& k = configs()[plan.cfg];
+    long useful = 0;
+    for (int i = 0; i < plan.n_strips; ++i) useful += plan.ux1[i] - plan.ux0[i];
+    return snprintf(buf, len,
+                    "cluster: patch %dx%d px/thread, %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
+                    "%d strip(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
+                    k.PR, k.PC, k.NW, k.RB(), k.TW(), plan.cs, plan.cs * k.RB(), plan.n_strips, (long)B * C * plan.n_strips,
+                    plan.max_clusters, (double)useful * H / ((double)plan.n_strips * k.TW() * plan.cs * k.RB()), k.smem);
+}
+
+int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
+    int dev = 0;
+    CSPN_CUDA_TRY(cudaGetDevice(&dev));
+    Plan plan;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        char why[200] = "";
+        if (!make_plan(p.B, p.C, p.H, p.W, p.iters, dev, plan, why, sizeof(why))) {
+            set_error("cluster kernel unsupported: %s", why);
+            return CSPN_ERR_UNSUPPORTED;
+        }
+        int rc = get_encode();
+        if (rc != CSPN_OK) return rc;
+    }
+    const KernelCfg& k = configs()[plan.cfg];
+
+    // guidance as a 3D tensor (W, H, B*gch); one box = (TW, RB, 1) floats of one channel plane
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)k.TW(), (cuuint32_t)k.RB(), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H, p.B * p.gch,
+                  k.TW(), k.RB());
+        return CSPN_ERR_CUDA;
+    }
+
+    ClusterParams prm;
+    prm.blur = p.blur; prm.sparse = p.sparse; prm.out = p.out;
+    prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = p.iters; prm.norm_abs = p.norm_abs;
+    prm.n_strips = plan.n_strips;
+    for (int i = 0; i < kMaxStrips; ++i) {
+        prm.tile_x0[i] = i < plan.n_strips ? plan.tile_x0[i] : 0;
+        prm.ux0[i] = i < plan.n_strips ? plan.ux0[i] : 0;
+        prm.ux1[i] = i < plan.n_strips ? plan.ux1[i] : 0;
+    }
+    const long tasks = (long)p.B * p.C * plan.n_strips;
+    if (tasks * plan.cs > 2147483647L) { set_error("grid too large"); return CSPN_ERR_UNSUPPORTED; }
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tasks * plan.cs));
+    cfg.blockDim = dim3(32 * k.NW);
+    cfg.dynamicSmemBytes = k.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = plan.cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void* args[2] = {(void*)&tm, (void*)&prm};
+    CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn, args));
+    ++*launches;
+    return CSPN_OK;
+}
+
 }  // namespace cspn
