@@ -124,7 +124,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 
 // ---- kernel ---------------------------------------------------------------------------------------
 // Shared memory map (dynamic):
-//   [0, 8*RB*TW*4)            stage: 8 gathered-affinity planes [k][RB][TW]   (TMA destination, 128 B aligned)
+//   [0, 8*RB*TWP*4)           stage: 8 guidance planes [k][RB][TWP], TWP = TW + 8: the box of channel k starts at
+//                             column tile_x0-4 (TMA needs a 16-byte aligned innermost origin, so the +-1 column
+//                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
 //   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
 //   then 3 mbarriers          tma, full[0], full[1]
 template <int PR, int PC, int NW>
@@ -132,21 +134,32 @@ struct Cfg {
     static constexpr int kThreads = 32 * NW;
     static constexpr int RB = NW * PR;   // rows per CTA band
     static constexpr int TW = 32 * PC;   // tile (strip) width
+    static constexpr int TWP = TW + 8;   // staged row pitch: 4 apron columns on each side
     static constexpr int kSlots = 2 * NW + 2;
-    static constexpr size_t kStageBytes = (size_t)8 * RB * TW * sizeof(float);
-    static constexpr size_t kXchBytes = (size_t)2 * kSlots * TW * sizeof(float);
+    static constexpr size_t kPlaneBytes = (size_t)RB * TWP * sizeof(float);
+    static constexpr size_t kStageBytes = 8 * kPlaneBytes;
+    static constexpr size_t kXchParityBytes = (size_t)kSlots * TW * sizeof(float);
+    static constexpr size_t kXchBytes = 2 * kXchParityBytes;
     static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + 64;
-    static_assert(PC % 2 == 0 && PC <= 8, "PC must be 2, 4, 6 or 8 (TMA box <= 256 columns)");
-    static_assert(RB <= 256, "TMA box rows");
+    static_assert(PC % 2 == 0 && TWP <= 256, "PC must be 2, 4 or 6 (TMA box <= 256 columns)");
+    static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));   // 1/0 = inf, so 0 * (1/0) = NaN like the reference's 0/0
+    return r;
+}
+
 // Row vector of PC pixels with its two x-neighbours: e[0] = left, e[1..PC] = own, e[PC+1] = right.
+// Outside the tile the neighbour is 0: either the image border (zero padding) or strip halo that decays.
 template <int PC>
-__device__ __forceinline__ void extend_row(const float (&v)[PC], float (&e)[PC + 2], int lane) {
-    float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
-    float r = __shfl_down_sync(0xffffffffu, v[0], 1);
-    e[0] = (lane == 0) ? 0.f : l;    // outside the tile: treated as 0 (image border, or strip halo that decays)
-    e[PC + 1] = (lane == 31) ? 0.f : r;
+__device__ __forceinline__ void extend_row(const float (&v)[PC], float (&e)[PC + 2], bool first_lane, bool last_lane) {
+    const float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+    const float r = __shfl_down_sync(0xffffffffu, v[0], 1);
+    e[0] = first_lane ? 0.f : l;
+    e[PC + 1] = last_lane ? 0.f : r;
 #pragma unroll
     for (int j = 0; j < PC; ++j) e[j + 1] = v[j];
 }
@@ -209,16 +222,81 @@ __device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)
     }
 }
 
-template <int PR, int PC, int NW>
+// Per-thread constants of the row exchange.
+struct Xch {
+    float* base;          // xch + lane*PC (parity 0, slot 0)
+    uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
+    uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
+    uint32_t up_rank, dn_rank;
+    bool has_up, has_dn, first_lane, last_lane, signal_lane;
+};
+
+// Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
+// halo slots through DSMEM), then signal full[PAR].
+template <int PR, int PC, int NW, int PAR>
+__device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
+    using K = Cfg<PR, PC, NW>;
+    float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
+    store_row_smem<PC>(p + (1 + 2 * wy) * K::TW, top);
+    store_row_smem<PC>(p + (2 + 2 * wy) * K::TW, bot);
+    const uint32_t bar = x.bar_full0 + 8 * PAR;
+    if (wy == 0 && x.has_up)        // my top row is the "halo from below" (last slot) of the CTA above
+        store_row_remote<PC>(map_to_cta(smem_u32(p + (K::kSlots - 1) * K::TW), x.up_rank), top, map_to_cta(bar, x.up_rank));
+    if (wy == NW - 1 && x.has_dn)   // my bottom row is the "halo from above" (slot 0) of the CTA below
+        store_row_remote<PC>(map_to_cta(smem_u32(p), x.dn_rank), bot, map_to_cta(bar, x.dn_rank));
+    __syncwarp();
+    if (x.signal_lane) {
+        if (wy == 0 && x.rx_bytes) mbar_arrive_expect_tx(bar, x.rx_bytes);
+        else mbar_arrive(bar);
+    }
+}
+
+// One propagation step d_it -> d_{it+1}; reads exchange buffer PAR, publishes into PAR^1.
+template <int PR, int PC, int NW, int PAR>
+__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bool last, const float (&w)[PR][PC][8],
+                                        const float (&c)[PR][PC], float (&d)[PR][PC]) {
+    using K = Cfg<PR, PC, NW>;
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+    // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
+    float up[PC + 2], dn[PC + 2], e[PR][PC + 2];
+    {
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
+        float t[PC];
+        load_row_smem<PC>(p + (2 * wy) * K::TW, t);        // row above my patch
+        extend_row<PC>(t, up, x.first_lane, x.last_lane);
+        load_row_smem<PC>(p + (2 * wy + 3) * K::TW, t);    // row below my patch
+        extend_row<PC>(t, dn, x.first_lane, x.last_lane);
+    }
+#pragma unroll
+    for (int r = 0; r < PR; ++r) extend_row<PC>(d[r], e[r], x.first_lane, x.last_lane);
+    // boundary rows first: they go out to the neighbours (shared memory / DSMEM) and the latency of that exchange
+    // hides behind the interior rows computed afterwards
+    float new_top[PC], new_bot[PC];
+    if constexpr (PR == 1) {
+        stencil_row<PC>(w[0], c[0], up, e[0], dn, new_top);
+#pragma unroll
+        for (int j = 0; j < PC; ++j) new_bot[j] = new_top[j];
+    } else {
+        stencil_row<PC>(w[0], c[0], up, e[0], e[1], new_top);
+        stencil_row<PC>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, new_bot);
+    }
+    if (!last) publish<PR, PC, NW, PAR ^ 1>(x, wy, new_top, new_bot);
+#pragma unroll
+    for (int r = 1; r <= PR - 2; ++r) stencil_row<PC>(w[r], c[r], e[r - 1], e[r], e[r + 1], d[r]);
+#pragma unroll
+    for (int j = 0; j < PC; ++j) { d[0][j] = new_top[j]; d[PR - 1][j] = new_bot[j]; }
+}
+
+template <int PR, int PC, int NW, bool ABS>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
     using K = Cfg<PR, PC, NW>;
-    constexpr int RB = K::RB, TW = K::TW;
+    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes);
-    const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1), bar_full1 = smem_u32(bars + 2);
+    const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
@@ -229,22 +307,29 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const int H = prm.H, W = prm.W;
     const int tile_x0 = prm.tile_x0[strip];
     const int band_y0 = (int)crank * RB;
-    const bool has_up = crank > 0, has_dn = crank + 1 < csize;
 
-    // bytes of halo rows this CTA RECEIVES per exchange (one row of TW floats from each existing neighbour)
-    const uint32_t rx_bytes = (uint32_t)((has_up ? 1 : 0) + (has_dn ? 1 : 0)) * TW * sizeof(float);
+    Xch xc;
+    xc.base = xch + lane * PC;
+    xc.bar_full0 = bar_full0;
+    xc.has_up = crank > 0;
+    xc.has_dn = crank + 1 < csize;
+    xc.up_rank = crank - 1;
+    xc.dn_rank = crank + 1;
+    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
+    xc.first_lane = lane == 0;
+    xc.last_lane = lane == 31;
+    xc.signal_lane = lane == 0;
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
         mbar_init(bar_full0, NW);
-        mbar_init(bar_full1, NW);
+        mbar_init(bar_full0 + 8, NW);
         fence_barrier_init();
         fence_proxy_async();
-        // a band that starts below the image has nothing to load (its pixels are all masked out)
         mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            tma_load_3d(smem_u32(stage + (size_t)k * RB * TW), &tm_guidance, tile_x0 + off2_dx(k), band_y0 + off2_dy(k),
+        for (int k = 0; k < 8; ++k)  // rows shifted by dy_k; out-of-image rows / columns arrive as zeros (= ZeroPad2d)
+            tma_load_3d(smem_u32(stage) + (uint32_t)(k * K::kPlaneBytes), &tm_guidance, tile_x0 - 4, band_y0 + off2_dy(k),
                         b * prm.gch + k, bar_tma);
     }
     // every CTA's barriers must be initialised before a neighbour's st.async can target them
@@ -278,108 +363,80 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         }
     }
 
-    cluster_wait();
-    mbar_wait(bar_tma, 0);
-
-    // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-        const int y = y_thr + r;
-        float a[8][PC];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) load_row_smem<PC>(stage + ((size_t)k * RB + wy * PR + r) * TW + lane * PC, a[k]);
-#pragma unroll
-        for (int j = 0; j < PC; ++j) {
-            const int x = x_thr + j;
-            const bool in = (y < H) && (x >= 0) && (x < W);
-            float S = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (prm.norm_abs) a[k][j] = fabsf(a[k][j]);
-                S += fabsf(a[k][j]);
-            }
-            const float inv = __frcp_rn(S);  // 1/0 = inf, 0*inf = NaN: the reference's 0/0 (cspn.py:138)
-            const float om = 1.f - m[r][j];
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float wk = a[k][j] * inv;
-                s += wk;
-                w[r][j][k] = in ? om * wk : 0.f;
-            }
-            const float kappa = om * (1.f - s) + m[r][j];
-            c[r][j] = in ? kappa * d[r][j] : 0.f;
-        }
-    }
-
-    // ---- exchange-buffer helpers -------------------------------------------------------------------
-    // slot 0: halo row from the CTA above; slots 1+2wy / 2+2wy: top / bottom row of warp wy; last: halo from below
-    auto xrow = [&](int parity, int slot) { return xch + ((size_t)parity * K::kSlots + slot) * TW + lane * PC; };
-    const uint32_t up_rank = crank - 1, dn_rank = crank + 1;
-
-    // publish boundary rows of the current d into buffer `parity` and signal full[parity]
-    auto publish = [&](int parity, const float (&top)[PC], const float (&bot)[PC]) {
-        store_row_smem<PC>(xrow(parity, 1 + 2 * wy), top);
-        store_row_smem<PC>(xrow(parity, 2 + 2 * wy), bot);
-        const uint32_t bar_local = parity ? bar_full1 : bar_full0;
-        if (wy == 0 && has_up)  // my top row is the "halo from below" of the CTA above
-            store_row_remote<PC>(map_to_cta(smem_u32(xrow(parity, K::kSlots - 1)), up_rank), top, map_to_cta(bar_local, up_rank));
-        if (wy == NW - 1 && has_dn)  // my bottom row is the "halo from above" of the CTA below
-            store_row_remote<PC>(map_to_cta(smem_u32(xrow(parity, 0)), dn_rank), bot, map_to_cta(bar_local, dn_rank));
-        __syncwarp();
-        if (lane == 0) {
-            if (wy == 0 && rx_bytes) mbar_arrive_expect_tx(bar_local, rx_bytes);
-            else mbar_arrive(bar_local);
-        }
-    };
-
     // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
-    if (!has_up) {
+    if (!xc.has_up)
         for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
-    }
-    if (!has_dn) {
+    if (!xc.has_dn)
         for (int i = tid; i < TW; i += K::kThreads) {
             xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
             xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
         }
-    }
-    __syncthreads();  // zeroed halo slots visible; everybody is done reading `stage`
 
-    const int iters = prm.iters;
-    if (iters > 0) publish(0, d[0], d[PR - 1]);
+    cluster_wait();
+    mbar_wait(bar_tma, 0);
+
+    // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
+    // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box, dx_k is applied here: the thread reads its own PC
+    // columns of plane k and takes the missing neighbour column from the next / previous lane (tile edge lanes read
+    // the apron column of the staged row instead).
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+        const int y = y_thr + r;
+        float S[PC], A[PC];
+#pragma unroll
+        for (int j = 0; j < PC; ++j) { S[j] = 0.f; A[j] = 0.f; }
+        float a[8][PC];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
+            float v[PC];
+            load_row_smem<PC>(row, v);
+            constexpr int kDx[8] = {1, 0, -1, 1, -1, 1, 0, -1};
+            if (kDx[k] == 1) {
+                float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+                if (lane == 31) nb = row[PC];
+#pragma unroll
+                for (int j = 0; j < PC - 1; ++j) a[k][j] = v[j + 1];
+                a[k][PC - 1] = nb;
+            } else if (kDx[k] == -1) {
+                float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+                if (lane == 0) nb = row[-1];
+#pragma unroll
+                for (int j = PC - 1; j > 0; --j) a[k][j] = v[j - 1];
+                a[k][0] = nb;
+            } else {
+#pragma unroll
+                for (int j = 0; j < PC; ++j) a[k][j] = v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < PC; ++j) {
+                if (ABS) a[k][j] = fabsf(a[k][j]);        // cspn.py:88-89
+                S[j] += fabsf(a[k][j]);                    // cspn.py:135-136
+                A[j] += a[k][j];                           // numerator of gate_sum, cspn.py:139
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PC; ++j) {
+            const int x = x_thr + j;
+            const bool in = (y < H) && (x >= 0) && (x < W);
+            const float inv = rcp_approx(S[j]);
+            const float om = 1.f - m[r][j];
+            const float scale = in ? om * inv : 0.f;          // pixels outside the image: w = 0, c = 0, d = 0 forever
+            const float kappa = om * (1.f - A[j] * inv) + m[r][j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
+            c[r][j] = in ? kappa * d[r][j] : 0.f;
+        }
+    }
+    __syncthreads();  // zeroed halo slots visible
 
     // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
-    for (int it = 0; it < iters; ++it) {
-        const int par = it & 1;
-        mbar_wait(par ? bar_full1 : bar_full0, (uint32_t)((it >> 1) & 1));
-
-        // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
-        float up[PC + 2], dn[PC + 2], e[PR][PC + 2];
-        {
-            float t[PC];
-            load_row_smem<PC>(xrow(par, 2 * wy), t);      // row above my patch
-            extend_row<PC>(t, up, lane);
-            load_row_smem<PC>(xrow(par, 2 * wy + 3), t);  // row below my patch
-            extend_row<PC>(t, dn, lane);
-        }
-#pragma unroll
-        for (int r = 0; r < PR; ++r) extend_row<PC>(d[r], e[r], lane);
-        // boundary rows first: they go out to the neighbours (shared memory / DSMEM) and the latency of that
-        // exchange hides behind the interior rows computed afterwards
-        float new_top[PC], new_bot[PC];
-        if constexpr (PR == 1) {
-            stencil_row<PC>(w[0], c[0], up, e[0], dn, new_top);
-#pragma unroll
-            for (int j = 0; j < PC; ++j) new_bot[j] = new_top[j];
-        } else {
-            stencil_row<PC>(w[0], c[0], up, e[0], e[1], new_top);
-            stencil_row<PC>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, new_bot);
-        }
-        if (it + 1 < iters) publish(par ^ 1, new_top, new_bot);
-#pragma unroll
-        for (int r = 1; r <= PR - 2; ++r) stencil_row<PC>(w[r], c[r], e[r - 1], e[r], e[r + 1], d[r]);
-#pragma unroll
-        for (int j = 0; j < PC; ++j) { d[0][j] = new_top[j]; d[PR - 1][j] = new_bot[j]; }
+    const int iters = prm.iters;
+    publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+    for (int it = 0; it < iters; it += 2) {
+        const uint32_t phase = (uint32_t)((it >> 1) & 1);
+        iterate<PR, PC, NW, 0>(xc, wy, phase, it + 1 == iters, w, c, d);
+        if (it + 1 < iters) iterate<PR, PC, NW, 1>(xc, wy, phase, it + 2 == iters, w, c, d);
     }
 
     // ---- epilogue: useful columns straight to global ------------------------------------------------
@@ -415,7 +472,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
 struct KernelCfg {
     int PR, PC, NW;
-    const void* fn;
+    const void* fn[2];  // [norm_abs]
     size_t smem;
     int RB() const { return PR * NW; }
     int TW() const { return 32 * PC; }
@@ -423,7 +480,9 @@ struct KernelCfg {
 
 template <int PR, int PC, int NW>
 KernelCfg make_cfg() {
-    return KernelCfg{PR, PC, NW, (const void*)&cspn2d_cluster_kernel<PR, PC, NW>, Cfg<PR, PC, NW>::kSmemBytes};
+    return KernelCfg{PR, PC, NW,
+                     {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true>},
+                     Cfg<PR, PC, NW>::kSmemBytes};
 }
 
 // The menu the planner picks from.  Register budget: 10 registers per pixel of state; PR*PC <= 20 pixels
@@ -433,7 +492,6 @@ const std::vector<KernelCfg>& configs() {
         make_cfg<5, 4, 8>(),   // 40 rows x 128 cols, 256 thr, 20 px/thread
         make_cfg<4, 4, 8>(),   // 32 x 128
         make_cfg<3, 6, 8>(),   // 24 x 192
-        make_cfg<2, 8, 8>(),   // 16 x 256
         make_cfg<2, 4, 8>(),   // 16 x 128 (small images)
     };
     return v;
@@ -457,11 +515,12 @@ int max_active_clusters(int ci, int cs, int dev) {
         if (e.first.cfg == ci && e.first.cs == cs && e.first.dev == dev) return e.second;
     const KernelCfg& k = configs()[ci];
     if (!g_attr_set[dev & 15][ci]) {
-        if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
-            cudaFuncSetAttribute(k.fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
+        for (int ab = 0; ab < 2; ++ab)
+            if (cudaFuncSetAttribute(k.fn[ab], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k.fn[ab], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                cudaGetLastError();
+                return 0;
+            }
         g_attr_set[dev & 15][ci] = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -476,7 +535,7 @@ int max_active_clusters(int ci, int cs, int dev) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k.fn, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, k.fn[0], &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
     g_occ_cache.push_back({OccKey{ci, cs, dev}, n});
     return n;
 }
@@ -603,7 +662,7 @@ int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
     CUtensorMap tm;
     const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
     const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)k.TW(), (cuuint32_t)k.RB(), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -639,7 +698,7 @@ int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     void* args[2] = {(void*)&tm, (void*)&prm};
-    CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn, args));
+    CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn[p.norm_abs ? 1 : 0], args));
     ++*launches;
     return CSPN_OK;
 }
