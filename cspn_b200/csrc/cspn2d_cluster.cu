@@ -227,7 +227,9 @@ struct Xch {
     float* base;          // xch + lane*PC (parity 0, slot 0)
     uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
     uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
-    uint32_t up_rank, dn_rank;
+    // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
+    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
+    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
     bool has_up, has_dn, first_lane, last_lane, signal_lane;
 };
 
@@ -241,9 +243,9 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     store_row_smem<PC>(p + (2 + 2 * wy) * K::TW, bot);
     const uint32_t bar = x.bar_full0 + 8 * PAR;
     if (wy == 0 && x.has_up)        // my top row is the "halo from below" (last slot) of the CTA above
-        store_row_remote<PC>(map_to_cta(smem_u32(p + (K::kSlots - 1) * K::TW), x.up_rank), top, map_to_cta(bar, x.up_rank));
+        store_row_remote<PC>(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
     if (wy == NW - 1 && x.has_dn)   // my bottom row is the "halo from above" (slot 0) of the CTA below
-        store_row_remote<PC>(map_to_cta(smem_u32(p), x.dn_rank), bot, map_to_cta(bar, x.dn_rank));
+        store_row_remote<PC>(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
     __syncwarp();
     if (x.signal_lane) {
         if (wy == 0 && x.rx_bytes) mbar_arrive_expect_tx(bar, x.rx_bytes);
@@ -251,10 +253,11 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     }
 }
 
-// One propagation step d_it -> d_{it+1}; reads exchange buffer PAR, publishes into PAR^1.
+// One propagation step d_it (din) -> d_{it+1} (dout); reads exchange buffer PAR, publishes into PAR^1.  Two register
+// sets alternate as input and output, so no value is ever copied between iterations.
 template <int PR, int PC, int NW, int PAR>
 __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bool last, const float (&w)[PR][PC][8],
-                                        const float (&c)[PR][PC], float (&d)[PR][PC]) {
+                                        const float (&c)[PR][PC], const float (&din)[PR][PC], float (&dout)[PR][PC]) {
     using K = Cfg<PR, PC, NW>;
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
     // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
@@ -268,23 +271,18 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bo
         extend_row<PC>(t, dn, x.first_lane, x.last_lane);
     }
 #pragma unroll
-    for (int r = 0; r < PR; ++r) extend_row<PC>(d[r], e[r], x.first_lane, x.last_lane);
+    for (int r = 0; r < PR; ++r) extend_row<PC>(din[r], e[r], x.first_lane, x.last_lane);
     // boundary rows first: they go out to the neighbours (shared memory / DSMEM) and the latency of that exchange
     // hides behind the interior rows computed afterwards
-    float new_top[PC], new_bot[PC];
     if constexpr (PR == 1) {
-        stencil_row<PC>(w[0], c[0], up, e[0], dn, new_top);
-#pragma unroll
-        for (int j = 0; j < PC; ++j) new_bot[j] = new_top[j];
+        stencil_row<PC>(w[0], c[0], up, e[0], dn, dout[0]);
     } else {
-        stencil_row<PC>(w[0], c[0], up, e[0], e[1], new_top);
-        stencil_row<PC>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, new_bot);
+        stencil_row<PC>(w[0], c[0], up, e[0], e[1], dout[0]);
+        stencil_row<PC>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, dout[PR - 1]);
     }
-    if (!last) publish<PR, PC, NW, PAR ^ 1>(x, wy, new_top, new_bot);
+    if (!last) publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
 #pragma unroll
-    for (int r = 1; r <= PR - 2; ++r) stencil_row<PC>(w[r], c[r], e[r - 1], e[r], e[r + 1], d[r]);
-#pragma unroll
-    for (int j = 0; j < PC; ++j) { d[0][j] = new_top[j]; d[PR - 1][j] = new_bot[j]; }
+    for (int r = 1; r <= PR - 2; ++r) stencil_row<PC>(w[r], c[r], e[r - 1], e[r], e[r + 1], dout[r]);
 }
 
 template <int PR, int PC, int NW, bool ABS>
@@ -313,8 +311,10 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.bar_full0 = bar_full0;
     xc.has_up = crank > 0;
     xc.has_dn = crank + 1 < csize;
-    xc.up_rank = crank - 1;
-    xc.dn_rank = crank + 1;
+    xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
+    xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
+    xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
+    xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
     xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
@@ -433,10 +433,17 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
     const int iters = prm.iters;
     publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+    float d2[PR][PC];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
     for (int it = 0; it < iters; it += 2) {
         const uint32_t phase = (uint32_t)((it >> 1) & 1);
-        iterate<PR, PC, NW, 0>(xc, wy, phase, it + 1 == iters, w, c, d);
-        if (it + 1 < iters) iterate<PR, PC, NW, 1>(xc, wy, phase, it + 2 == iters, w, c, d);
+        iterate<PR, PC, NW, 0>(xc, wy, phase, it + 1 == iters, w, c, d, d2);
+        if (it + 1 < iters) iterate<PR, PC, NW, 1>(xc, wy, phase, it + 2 == iters, w, c, d2, d);
+    }
+    if (iters & 1) {
+#pragma unroll
+        for (int r = 0; r < PR; ++r)
+#pragma unroll
+            for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
     }
 
     // ---- epilogue: useful columns straight to global ------------------------------------------------
