@@ -44,7 +44,7 @@ struct ClusterParams {
     const float* sparse;  // [B][H][W] or null
     float* out;           // [B*C][H][W]
     int C, H, W, gch, iters, norm_abs;
-    int n_strips;
+    int n_strips, n_tasks;
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -95,6 +95,11 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ uint32_t cluster_id_x() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nclusterid_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
     return r;
 }
 // shared::cta address -> shared::cluster address of the same offset in CTA `rank`
@@ -298,13 +303,10 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-    const int task = (int)cluster_id_x();
-    const int strip = task % prm.n_strips;
-    const int bc = task / prm.n_strips;  // b*C + c
-    const int b = bc / prm.C;
     const int H = prm.H, W = prm.W;
-    const int tile_x0 = prm.tile_x0[strip];
     const int band_y0 = (int)crank * RB;
+    const int y_thr = band_y0 + wy * PR;    // first row of this thread
+    const size_t HW = (size_t)H * W;
 
     Xch xc;
     xc.base = xch + lane * PC;
@@ -320,49 +322,33 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.last_lane = lane == 31;
     xc.signal_lane = lane == 0;
 
+    // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
+    const int n_tasks = prm.n_tasks;
+    const int task_stride = (int)cluster_nclusterid_x();
+    int task = (int)cluster_id_x();
+
+    // Stage the 8 guidance planes of one task: rows shifted by dy_k ride on the box origin; out-of-image rows and
+    // columns arrive as zeros (= ZeroPad2d, cspn.py:105-129).
+    auto issue_stage = [&](int t) {
+        const int strip_t = t % prm.n_strips;
+        const int b_t = (t / prm.n_strips) / prm.C;
+        mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            tma_load_3d(smem_u32(stage) + (uint32_t)(k * K::kPlaneBytes), &tm_guidance, prm.tile_x0[strip_t] - 4,
+                        band_y0 + off2_dy(k), b_t * prm.gch + k, bar_tma);
+    };
+
     if (tid == 0) {
         mbar_init(bar_tma, 1);
         mbar_init(bar_full0, NW);
         mbar_init(bar_full0 + 8, NW);
         fence_barrier_init();
         fence_proxy_async();
-        mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // rows shifted by dy_k; out-of-image rows / columns arrive as zeros (= ZeroPad2d)
-            tma_load_3d(smem_u32(stage) + (uint32_t)(k * K::kPlaneBytes), &tm_guidance, tile_x0 - 4, band_y0 + off2_dy(k),
-                        b * prm.gch + k, bar_tma);
+        if (task < n_tasks) issue_stage(task);
     }
     // every CTA's barriers must be initialised before a neighbour's st.async can target them
     cluster_arrive();
-
-    // ---- thread state ---------------------------------------------------------------------------
-    float w[PR][PC][8], c[PR][PC], d[PR][PC];
-    const int x_thr = tile_x0 + lane * PC;  // first column of this thread
-    const int y_thr = band_y0 + wy * PR;    // first row of this thread
-    const size_t HW = (size_t)H * W;
-    const float* blur = prm.blur + (size_t)bc * HW;
-    const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
-
-    // blur / sparse: straight from global (aligned, read once); overlaps with the TMA in flight
-    float m[PR][PC];
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-        const int y = y_thr + r;
-#pragma unroll
-        for (int q = 0; q < PC / 2; ++q) {
-            const int x = x_thr + 2 * q;
-            // W % 4 == 0 and x even: a float2 is entirely inside or outside the image
-            const bool in = (y < H) && (x >= 0) && (x < W);
-            float2 dv = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
-            if (in) {
-                dv = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + x));
-                if (sparse) sv = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + x));
-            }
-            d[r][2 * q] = dv.x; d[r][2 * q + 1] = dv.y;
-            m[r][2 * q] = signf(sv.x); m[r][2 * q + 1] = signf(sv.y);
-        }
-    }
-
     // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
     if (!xc.has_up)
         for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
@@ -371,108 +357,175 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
             xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
         }
-
     cluster_wait();
-    mbar_wait(bar_tma, 0);
 
-    // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
-    // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box, dx_k is applied here: the thread reads its own PC
-    // columns of plane k and takes the missing neighbour column from the next / previous lane (tile edge lanes read
-    // the apron column of the staged row instead).
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-        const int y = y_thr + r;
-        float S[PC], A[PC];
-#pragma unroll
-        for (int j = 0; j < PC; ++j) { S[j] = 0.f; A[j] = 0.f; }
-        float a[8][PC];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
-            float v[PC];
-            load_row_smem<PC>(row, v);
-            constexpr int kDx[8] = {1, 0, -1, 1, -1, 1, 0, -1};
-            if (kDx[k] == 1) {
-                float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
-                if (lane == 31) nb = row[PC];
-#pragma unroll
-                for (int j = 0; j < PC - 1; ++j) a[k][j] = v[j + 1];
-                a[k][PC - 1] = nb;
-            } else if (kDx[k] == -1) {
-                float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
-                if (lane == 0) nb = row[-1];
-#pragma unroll
-                for (int j = PC - 1; j > 0; --j) a[k][j] = v[j - 1];
-                a[k][0] = nb;
-            } else {
-#pragma unroll
-                for (int j = 0; j < PC; ++j) a[k][j] = v[j];
-            }
-#pragma unroll
-            for (int j = 0; j < PC; ++j) {
-                if (ABS) a[k][j] = fabsf(a[k][j]);        // cspn.py:88-89
-                S[j] += fabsf(a[k][j]);                    // cspn.py:135-136
-                A[j] += a[k][j];                           // numerator of gate_sum, cspn.py:139
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < PC; ++j) {
-            const int x = x_thr + j;
-            const bool in = (y < H) && (x >= 0) && (x < W);
-            const float inv = rcp_approx(S[j]);
-            const float om = 1.f - m[r][j];
-            const float scale = in ? om * inv : 0.f;          // pixels outside the image: w = 0, c = 0, d = 0 forever
-            const float kappa = om * (1.f - A[j] * inv) + m[r][j];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
-            c[r][j] = in ? kappa * d[r][j] : 0.f;
-        }
-    }
-    __syncthreads();  // zeroed halo slots visible
+    uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
+    bool first = true;
+    for (; task < n_tasks; task += task_stride) {
+        const int strip = task % prm.n_strips;
+        const int bc = task / prm.n_strips;  // b*C + c
+        const int b = bc / prm.C;
+        const int tile_x0 = prm.tile_x0[strip];
+        const int x_thr = tile_x0 + lane * PC;  // first column of this thread
 
-    // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
-    const int iters = prm.iters;
-    publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
-    float d2[PR][PC];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
-    for (int it = 0; it < iters; it += 2) {
-        const uint32_t phase = (uint32_t)((it >> 1) & 1);
-        iterate<PR, PC, NW, 0>(xc, wy, phase, it + 1 == iters, w, c, d, d2);
-        if (it + 1 < iters) iterate<PR, PC, NW, 1>(xc, wy, phase, it + 2 == iters, w, c, d2, d);
-    }
-    if (iters & 1) {
-#pragma unroll
-        for (int r = 0; r < PR; ++r)
-#pragma unroll
-            for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
-    }
+        // ---- thread state ---------------------------------------------------------------------------
+        float w[PR][PC][8], c[PR][PC], d[PR][PC];
+        const float* blur = prm.blur + (size_t)bc * HW;
+        const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
 
-    // ---- epilogue: useful columns straight to global ------------------------------------------------
-    float* out = prm.out + (size_t)bc * HW;
-    const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
+        // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2)
+        float m[PR][PC];
 #pragma unroll
-    for (int r = 0; r < PR; ++r) {
-        const int y = y_thr + r;
-        if (y >= H) continue;
-        if constexpr (PC % 4 == 0) {
-#pragma unroll
-            for (int q = 0; q < PC / 4; ++q) {
-                const int x = x_thr + 4 * q;
-                if (x >= ux0 && x < ux1)
-                    __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x),
-                           make_float4(d[r][4 * q], d[r][4 * q + 1], d[r][4 * q + 2], d[r][4 * q + 3]));
-            }
-        } else {
+        for (int r = 0; r < PR; ++r) {
+            const int y = y_thr + r;
 #pragma unroll
             for (int q = 0; q < PC / 2; ++q) {
                 const int x = x_thr + 2 * q;
-                if (x >= ux0 && x < ux1)
-                    __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + x), make_float2(d[r][2 * q], d[r][2 * q + 1]));
+                // W % 4 == 0 and x even: a float2 is entirely inside or outside the image
+                const bool in = (y < H) && (x >= 0) && (x < W);
+                float2 dv = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
+                if (in) {
+                    dv = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + x));
+                    if (sparse) sv = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + x));
+                }
+                d[r][2 * q] = dv.x; d[r][2 * q + 1] = dv.y;
+                m[r][2 * q] = signf(sv.x); m[r][2 * q + 1] = signf(sv.y);
+            }
+        }
+
+        mbar_wait(bar_tma, ph_tma);
+        ph_tma ^= 1;
+
+        // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
+        // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box, dx_k is applied here: the thread reads its own
+        // PC columns of plane k and takes the missing neighbour column from the next / previous lane (tile edge
+        // lanes read the apron column of the staged row instead).
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+            const int y = y_thr + r;
+            float S[PC], A[PC];
+#pragma unroll
+            for (int j = 0; j < PC; ++j) { S[j] = 0.f; A[j] = 0.f; }
+            float a[8][PC];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
+                float v[PC];
+                load_row_smem<PC>(row, v);
+                constexpr int kDx[8] = {1, 0, -1, 1, -1, 1, 0, -1};
+                if (kDx[k] == 1) {
+                    float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+                    if (lane == 31) nb = row[PC];
+#pragma unroll
+                    for (int j = 0; j < PC - 1; ++j) a[k][j] = v[j + 1];
+                    a[k][PC - 1] = nb;
+                } else if (kDx[k] == -1) {
+                    float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+                    if (lane == 0) nb = row[-1];
+#pragma unroll
+                    for (int j = PC - 1; j > 0; --j) a[k][j] = v[j - 1];
+                    a[k][0] = nb;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) a[k][j] = v[j];
+                }
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    if (ABS) a[k][j] = fabsf(a[k][j]);        // cspn.py:88-89
+                    S[j] += fabsf(a[k][j]);                    // cspn.py:135-136
+                    A[j] += a[k][j];                           // numerator of gate_sum, cspn.py:139
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PC; ++j) {
+                const int x = x_thr + j;
+                const bool in = (y < H) && (x >= 0) && (x < W);
+                const float inv = rcp_approx(S[j]);
+                const float om = 1.f - m[r][j];
+                const float scale = in ? om * inv : 0.f;      // pixels outside the image: w = 0, c = 0, d = 0 forever
+                const float kappa = om * (1.f - A[j] * inv) + m[r][j];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
+                c[r][j] = in ? kappa * d[r][j] : 0.f;
+            }
+        }
+        __syncthreads();  // every warp is done with the staging buffer
+
+        // ---- next task's guidance starts streaming in now; it lands while this task iterates in registers ----
+        const int next = task + task_stride;
+        if (next < n_tasks) {
+            if (tid == 0) {
+                fence_proxy_async();  // generic-proxy reads of `stage` above are ordered before the async-proxy writes
+                issue_stage(next);
+            }
+            // its blur / sparse rows: pull the lines into L2
+            const int strip_n = next % prm.n_strips, bc_n = next / prm.n_strips;
+            const int xn = prm.tile_x0[strip_n] + lane * PC;
+            // one lane per 128-byte line of the row segment this warp will read
+            const bool pf_lane = lane == 0 || ((lane - 1) * PC) / 32 != (lane * PC) / 32;
+            if (pf_lane && xn < W) {
+                const float* bn = prm.blur + (size_t)bc_n * HW;
+                const float* sn = prm.sparse ? prm.sparse + (size_t)(bc_n / prm.C) * HW : nullptr;
+#pragma unroll
+                for (int r = 0; r < PR; ++r) {
+                    const int y = y_thr + r;
+                    if (y < H) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + xn));
+                        if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + xn));
+                    }
+                }
+            }
+        }
+
+        // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
+        if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
+        first = false;
+        const int iters = prm.iters;
+        publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+        float d2[PR][PC];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
+        for (int it = 0; it < iters; it += 2) {
+            iterate<PR, PC, NW, 0>(xc, wy, ph0, it + 1 == iters, w, c, d, d2);
+            ph0 ^= 1;
+            if (it + 1 < iters) {
+                iterate<PR, PC, NW, 1>(xc, wy, ph1, it + 2 == iters, w, c, d2, d);
+                ph1 ^= 1;
+            }
+        }
+        cluster_arrive();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
+        if (iters & 1) {
+#pragma unroll
+            for (int r = 0; r < PR; ++r)
+#pragma unroll
+                for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
+        }
+
+        // ---- epilogue: useful columns straight to global ------------------------------------------------
+        float* out = prm.out + (size_t)bc * HW;
+        const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+            const int y = y_thr + r;
+            if (y >= H) continue;
+            if constexpr (PC % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < PC / 4; ++q) {
+                    const int x = x_thr + 4 * q;
+                    if (x >= ux0 && x < ux1)
+                        __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x),
+                               make_float4(d[r][4 * q], d[r][4 * q + 1], d[r][4 * q + 2], d[r][4 * q + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PC / 2; ++q) {
+                    const int x = x_thr + 2 * q;
+                    if (x >= ux0 && x < ux1)
+                        __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + x), make_float2(d[r][2 * q], d[r][2 * q + 1]));
+                }
             }
         }
     }
     // No CTA may exit while a neighbour could still address its shared memory.
-    cluster_arrive();
-    cluster_wait();
+    if (!first) cluster_wait();
 }
 
 // ---- host side: configurations, planner, launch ---------------------------------------------------
@@ -684,16 +737,19 @@ int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
     prm.blur = p.blur; prm.sparse = p.sparse; prm.out = p.out;
     prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = p.iters; prm.norm_abs = p.norm_abs;
     prm.n_strips = plan.n_strips;
+    prm.n_tasks = (int)((long)p.B * p.C * plan.n_strips);
     for (int i = 0; i < kMaxStrips; ++i) {
         prm.tile_x0[i] = i < plan.n_strips ? plan.tile_x0[i] : 0;
         prm.ux0[i] = i < plan.n_strips ? plan.ux0[i] : 0;
         prm.ux1[i] = i < plan.n_strips ? plan.ux1[i] : 0;
     }
     const long tasks = (long)p.B * p.C * plan.n_strips;
-    if (tasks * plan.cs > 2147483647L) { set_error("grid too large"); return CSPN_ERR_UNSUPPORTED; }
+    if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
+    // persistent clusters: as many as fit on the device at once, each looping over tasks
+    const long n_clusters = tasks < plan.max_clusters ? tasks : plan.max_clusters;
 
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tasks * plan.cs));
+    cfg.gridDim = dim3((unsigned)(n_clusters * plan.cs));
     cfg.blockDim = dim3(32 * k.NW);
     cfg.dynamicSmemBytes = k.smem;
     cfg.stream = stream;
