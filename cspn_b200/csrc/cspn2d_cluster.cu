@@ -62,6 +62,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// lane-predicated forms: no divergent branch (BSSY/BSYNC) around the single arriving lane
+__device__ __forceinline__ void mbar_arrive_if(uint32_t bar, bool pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"(bar), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t bar, uint32_t bytes, bool pred) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(bar), "r"(bytes), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -81,6 +88,8 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrival that only signals progress (no memory ordering needed: it guards buffers this CTA has finished READING)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -252,10 +261,8 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     if (wy == NW - 1 && x.has_dn)   // my bottom row is the "halo from above" (slot 0) of the CTA below
         store_row_remote<PC>(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
     __syncwarp();
-    if (x.signal_lane) {
-        if (wy == 0 && x.rx_bytes) mbar_arrive_expect_tx(bar, x.rx_bytes);
-        else mbar_arrive(bar);
-    }
+    if (wy == 0 && x.rx_bytes) mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.signal_lane);
+    else mbar_arrive_if(bar, x.signal_lane);
 }
 
 // One propagation step d_it (din) -> d_{it+1} (dout); reads exchange buffer PAR, publishes into PAR^1.  Two register
@@ -491,7 +498,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 ph1 ^= 1;
             }
         }
-        cluster_arrive();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
+        cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
         if (iters & 1) {
 #pragma unroll
             for (int r = 0; r < PR; ++r)
