@@ -137,25 +137,33 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
+// Thread patch and the FFMA2 pairing.  A tile is TW = 64*PCH columns wide.  Lane l owns, in each of its PR rows,
+// PCH columns of the LEFT half (PCH*l + j) and the PCH columns at the same offset in the RIGHT half
+// (TW/2 + PCH*l + j).  Pixel j of the left half and pixel j of the right half are kept together as one float2
+// (.x = left, .y = right): every stencil tap then reads an aligned register pair again, so the 8 FMAs of two
+// pixels issue as 8 FFMA2 (fma.rn.f32x2, new on sm_100) -- half the issue slots of scalar FFMA, which is what
+// bounds this kernel (FP32 pipe, not HBM, at 24 iterations).
+//
 // Shared memory map (dynamic):
 //   [0, 8*RB*TWP*4)           stage: 8 guidance planes [k][RB][TWP], TWP = TW + 8: the box of channel k starts at
 //                             column tile_x0-4 (TMA needs a 16-byte aligned innermost origin, so the +-1 column
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
-//   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
+//   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, lane-major pairs)
 //   then 3 mbarriers          tma, full[0], full[1]
-template <int PR, int PC, int NW>
+template <int PR, int PCH, int NW>
 struct Cfg {
     static constexpr int kThreads = 32 * NW;
-    static constexpr int RB = NW * PR;   // rows per CTA band
-    static constexpr int TW = 32 * PC;   // tile (strip) width
-    static constexpr int TWP = TW + 8;   // staged row pitch: 4 apron columns on each side
+    static constexpr int RB = NW * PR;    // rows per CTA band
+    static constexpr int TW = 64 * PCH;   // tile (strip) width
+    static constexpr int TWP = TW + 8;    // staged row pitch: 4 apron columns on each side
     static constexpr int kSlots = 2 * NW + 2;
     static constexpr size_t kPlaneBytes = (size_t)RB * TWP * sizeof(float);
     static constexpr size_t kStageBytes = 8 * kPlaneBytes;
     static constexpr size_t kXchParityBytes = (size_t)kSlots * TW * sizeof(float);
     static constexpr size_t kXchBytes = 2 * kXchParityBytes;
     static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + 64;
-    static_assert(PC % 2 == 0 && TWP <= 256, "PC must be 2, 4 or 6 (TMA box <= 256 columns)");
+    static_assert(PCH == 2, "vectorised global/shared accesses below assume 2 columns per half");
+    static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
@@ -166,100 +174,113 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// Row vector of PC pixels with its two x-neighbours: e[0] = left, e[1..PC] = own, e[PC+1] = right.
-// Outside the tile the neighbour is 0: either the image border (zero padding) or strip halo that decays.
-template <int PC>
-__device__ __forceinline__ void extend_row(const float (&v)[PC], float (&e)[PC + 2], bool first_lane, bool last_lane) {
-    const float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
-    const float r = __shfl_down_sync(0xffffffffu, v[0], 1);
-    e[0] = first_lane ? 0.f : l;
-    e[PC + 1] = last_lane ? 0.f : r;
+// A pixel pair lives in ONE 64-bit register (an aligned register pair) from the moment it is produced by FFMA2 until
+// it is consumed; halves are only named when a shuffle or a select needs a 32-bit value.
+typedef unsigned long long pair_t;
+__device__ __forceinline__ pair_t mk(float x, float y) {
+    pair_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float lo(pair_t p) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p));
+    return x;
+}
+__device__ __forceinline__ float hi(pair_t p) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p));
+    return y;
+}
+__device__ __forceinline__ pair_t ffma2(pair_t a, pair_t b, pair_t c) {
+    pair_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+struct LaneInfo {
+    int rot_prev, rot_next;   // (lane-1)&31, (lane+1)&31
+    bool first, last;         // lane 0 / lane 31
+};
+
+// Row of PCH pixel pairs with its two x-neighbour pairs: e[0] = left, e[1..PCH] = own, e[PCH+1] = right.
+//   left pair  = columns (PCH*l - 1,  TW/2 + PCH*l - 1):  lane l-1's last pair, except for lane 0, whose .x lies
+//                outside the tile (0: image border, or strip halo that decays) and whose .y is column TW/2-1,
+//                i.e. the .x of lane 31's last pair;
+//   right pair = columns (PCH*l + PCH, TW/2 + PCH*l + PCH): lane l+1's first pair, except for lane 31, whose .x is
+//                column TW/2 = the .y of lane 0's first pair and whose .y lies outside the tile.
+template <int PCH>
+__device__ __forceinline__ void extend_row(const pair_t (&v)[PCH], pair_t (&e)[PCH + 2], const LaneInfo& li) {
+    const float ax = lo(v[PCH - 1]), ay = hi(v[PCH - 1]), bx = lo(v[0]), by = hi(v[0]);
+    const float lx = __shfl_up_sync(0xffffffffu, ax, 1);
+    const float ly = __shfl_sync(0xffffffffu, li.last ? ax : ay, li.rot_prev);
+    const float rx = __shfl_sync(0xffffffffu, li.first ? by : bx, li.rot_next);
+    const float ry = __shfl_down_sync(0xffffffffu, by, 1);
+    e[0] = mk(li.first ? 0.f : lx, ly);
+    e[PCH + 1] = mk(rx, li.last ? 0.f : ry);
 #pragma unroll
-    for (int j = 0; j < PC; ++j) e[j + 1] = v[j];
+    for (int j = 0; j < PCH; ++j) e[j + 1] = v[j];
 }
 
 // new value of one row: c + sum_k w_k * neighbour_k ; up = row y-1, cur = row y, dn = row y+1 (extended rows)
-template <int PC>
-__device__ __forceinline__ void stencil_row(const float (&w)[PC][8], const float (&c)[PC], const float (&up)[PC + 2],
-                                            const float (&cur)[PC + 2], const float (&dn)[PC + 2], float (&o)[PC]) {
+template <int PCH>
+__device__ __forceinline__ void stencil_row(const pair_t (&w)[PCH][8], const pair_t (&c)[PCH], const pair_t (&up)[PCH + 2],
+                                            const pair_t (&cur)[PCH + 2], const pair_t (&dn)[PCH + 2], pair_t (&o)[PCH]) {
 #pragma unroll
-    for (int j = 0; j < PC; ++j) {
-        float acc = c[j];
-        acc = fmaf(w[j][0], dn[j + 2], acc);   // (+1,+1)
-        acc = fmaf(w[j][1], dn[j + 1], acc);   // (+1, 0)
-        acc = fmaf(w[j][2], dn[j], acc);       // (+1,-1)
-        acc = fmaf(w[j][3], cur[j + 2], acc);  // ( 0,+1)
-        acc = fmaf(w[j][4], cur[j], acc);      // ( 0,-1)
-        acc = fmaf(w[j][5], up[j + 2], acc);   // (-1,+1)
-        acc = fmaf(w[j][6], up[j + 1], acc);   // (-1, 0)
-        acc = fmaf(w[j][7], up[j], acc);       // (-1,-1)
+    for (int j = 0; j < PCH; ++j) {
+        pair_t acc = c[j];
+        acc = ffma2(w[j][0], dn[j + 2], acc);   // (+1,+1)
+        acc = ffma2(w[j][1], dn[j + 1], acc);   // (+1, 0)
+        acc = ffma2(w[j][2], dn[j], acc);       // (+1,-1)
+        acc = ffma2(w[j][3], cur[j + 2], acc);  // ( 0,+1)
+        acc = ffma2(w[j][4], cur[j], acc);      // ( 0,-1)
+        acc = ffma2(w[j][5], up[j + 2], acc);   // (-1,+1)
+        acc = ffma2(w[j][6], up[j + 1], acc);   // (-1, 0)
+        acc = ffma2(w[j][7], up[j], acc);       // (-1,-1)
         o[j] = acc;
     }
 }
 
-template <int PC>
-__device__ __forceinline__ void load_row_smem(const float* p, float (&v)[PC]) {
-    if constexpr (PC % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < PC / 4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
-            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < PC / 2; ++q) {
-            const float2 t = *reinterpret_cast<const float2*>(p + 2 * q);
-            v[2 * q] = t.x; v[2 * q + 1] = t.y;
-        }
-    }
+// exchange rows are stored lane-major: lane l's PCH pairs are 2*PCH consecutive floats at offset 2*PCH*l
+__device__ __forceinline__ void load_row_smem(const float* p, pair_t (&v)[2]) {
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
+    v[0] = t.x;
+    v[1] = t.y;
 }
-template <int PC>
-__device__ __forceinline__ void store_row_smem(float* p, const float (&v)[PC]) {
-    if constexpr (PC % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < PC / 4; ++q)
-            *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < PC / 2; ++q) *reinterpret_cast<float2*>(p + 2 * q) = make_float2(v[2 * q], v[2 * q + 1]);
-    }
+__device__ __forceinline__ void store_row_smem(float* p, const pair_t (&v)[2]) {
+    *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v[0], v[1]);
 }
-template <int PC>
-__device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)[PC], uint32_t bar) {
-    if constexpr (PC % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < PC / 4; ++q)
-            st_async_v4(addr + 16 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), bar);
-    } else {
-#pragma unroll
-        for (int q = 0; q < PC / 2; ++q) st_async_v2(addr + 8 * q, make_float2(v[2 * q], v[2 * q + 1]), bar);
-    }
+__device__ __forceinline__ void store_row_remote(uint32_t addr, const pair_t (&v)[2], uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(addr), "l"(v[0]),
+                 "l"(v[1]), "r"(bar)
+                 : "memory");
 }
 
 // Per-thread constants of the row exchange.
 struct Xch {
-    float* base;          // xch + lane*PC (parity 0, slot 0)
+    float* base;          // xch + lane's pair offset (parity 0, slot 0)
     uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
     uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
-    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
+    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's offset, its full[0]
     uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
-    bool has_up, has_dn, first_lane, last_lane, signal_lane;
+    bool has_up, has_dn, signal_lane;
+    LaneInfo li;
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
 // halo slots through DSMEM), then signal full[PAR].
-template <int PR, int PC, int NW, int PAR>
-__device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
-    using K = Cfg<PR, PC, NW>;
+template <int PR, int PCH, int NW, int PAR>
+__device__ __forceinline__ void publish(const Xch& x, int wy, const pair_t (&top)[PCH], const pair_t (&bot)[PCH]) {
+    using K = Cfg<PR, PCH, NW>;
     float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
-    store_row_smem<PC>(p + (1 + 2 * wy) * K::TW, top);
-    store_row_smem<PC>(p + (2 + 2 * wy) * K::TW, bot);
+    store_row_smem(p + (1 + 2 * wy) * K::TW, top);
+    store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
     const uint32_t bar = x.bar_full0 + 8 * PAR;
     if (wy == 0 && x.has_up)        // my top row is the "halo from below" (last slot) of the CTA above
-        store_row_remote<PC>(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
+        store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
     if (wy == NW - 1 && x.has_dn)   // my bottom row is the "halo from above" (slot 0) of the CTA below
-        store_row_remote<PC>(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
+        store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
     __syncwarp();
     if (wy == 0 && x.rx_bytes) mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.signal_lane);
     else mbar_arrive_if(bar, x.signal_lane);
@@ -267,41 +288,41 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
 
 // One propagation step d_it (din) -> d_{it+1} (dout); reads exchange buffer PAR, publishes into PAR^1.  Two register
 // sets alternate as input and output, so no value is ever copied between iterations.
-template <int PR, int PC, int NW, int PAR>
-__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bool last, const float (&w)[PR][PC][8],
-                                        const float (&c)[PR][PC], const float (&din)[PR][PC], float (&dout)[PR][PC]) {
-    using K = Cfg<PR, PC, NW>;
+template <int PR, int PCH, int NW, int PAR>
+__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bool last, const pair_t (&w)[PR][PCH][8],
+                                        const pair_t (&c)[PR][PCH], const pair_t (&din)[PR][PCH], pair_t (&dout)[PR][PCH]) {
+    using K = Cfg<PR, PCH, NW>;
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
     // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
-    float up[PC + 2], dn[PC + 2], e[PR][PC + 2];
+    pair_t up[PCH + 2], dn[PCH + 2], e[PR][PCH + 2];
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
-        float t[PC];
-        load_row_smem<PC>(p + (2 * wy) * K::TW, t);        // row above my patch
-        extend_row<PC>(t, up, x.first_lane, x.last_lane);
-        load_row_smem<PC>(p + (2 * wy + 3) * K::TW, t);    // row below my patch
-        extend_row<PC>(t, dn, x.first_lane, x.last_lane);
+        pair_t t[PCH];
+        load_row_smem(p + (2 * wy) * K::TW, t);        // row above my patch
+        extend_row<PCH>(t, up, x.li);
+        load_row_smem(p + (2 * wy + 3) * K::TW, t);    // row below my patch
+        extend_row<PCH>(t, dn, x.li);
     }
 #pragma unroll
-    for (int r = 0; r < PR; ++r) extend_row<PC>(din[r], e[r], x.first_lane, x.last_lane);
+    for (int r = 0; r < PR; ++r) extend_row<PCH>(din[r], e[r], x.li);
     // boundary rows first: they go out to the neighbours (shared memory / DSMEM) and the latency of that exchange
     // hides behind the interior rows computed afterwards
     if constexpr (PR == 1) {
-        stencil_row<PC>(w[0], c[0], up, e[0], dn, dout[0]);
+        stencil_row<PCH>(w[0], c[0], up, e[0], dn, dout[0]);
     } else {
-        stencil_row<PC>(w[0], c[0], up, e[0], e[1], dout[0]);
-        stencil_row<PC>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, dout[PR - 1]);
+        stencil_row<PCH>(w[0], c[0], up, e[0], e[1], dout[0]);
+        stencil_row<PCH>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, dout[PR - 1]);
     }
-    if (!last) publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+    if (!last) publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
 #pragma unroll
-    for (int r = 1; r <= PR - 2; ++r) stencil_row<PC>(w[r], c[r], e[r - 1], e[r], e[r + 1], dout[r]);
+    for (int r = 1; r <= PR - 2; ++r) stencil_row<PCH>(w[r], c[r], e[r - 1], e[r], e[r + 1], dout[r]);
 }
 
-template <int PR, int PC, int NW, bool ABS>
+template <int PR, int PCH, int NW, bool ABS>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
-    using K = Cfg<PR, PC, NW>;
-    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP;
+    using K = Cfg<PR, PCH, NW>;
+    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP, HALF = TW / 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
@@ -316,7 +337,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const size_t HW = (size_t)H * W;
 
     Xch xc;
-    xc.base = xch + lane * PC;
+    xc.base = xch + lane * 2 * PCH;
     xc.bar_full0 = bar_full0;
     xc.has_up = crank > 0;
     xc.has_dn = crank + 1 < csize;
@@ -325,9 +346,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
     xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
     xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
-    xc.first_lane = lane == 0;
-    xc.last_lane = lane == 31;
     xc.signal_lane = lane == 0;
+    xc.li.first = lane == 0;
+    xc.li.last = lane == 31;
+    xc.li.rot_prev = (lane + 31) & 31;
+    xc.li.rot_next = (lane + 1) & 31;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -373,87 +396,74 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const int bc = task / prm.n_strips;  // b*C + c
         const int b = bc / prm.C;
         const int tile_x0 = prm.tile_x0[strip];
-        const int x_thr = tile_x0 + lane * PC;  // first column of this thread
+        const int xl = tile_x0 + lane * PCH;  // first column of this thread in the left half; right half: + HALF
 
-        // ---- thread state ---------------------------------------------------------------------------
-        float w[PR][PC][8], c[PR][PC], d[PR][PC];
+        // ---- thread state: pairs (.x = left-half pixel, .y = right-half pixel) ---------------------------
+        pair_t w[PR][PCH][8], c[PR][PCH], d[PR][PCH];
+        float2 d0v[PR][PCH];
         const float* blur = prm.blur + (size_t)bc * HW;
         const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
 
         // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2)
-        float m[PR][PC];
+        float2 m[PR][PCH];
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
             const int y = y_thr + r;
-#pragma unroll
-            for (int q = 0; q < PC / 2; ++q) {
-                const int x = x_thr + 2 * q;
-                // W % 4 == 0 and x even: a float2 is entirely inside or outside the image
-                const bool in = (y < H) && (x >= 0) && (x < W);
-                float2 dv = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
-                if (in) {
-                    dv = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + x));
-                    if (sparse) sv = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + x));
-                }
-                d[r][2 * q] = dv.x; d[r][2 * q + 1] = dv.y;
-                m[r][2 * q] = signf(sv.x); m[r][2 * q + 1] = signf(sv.y);
+            // W % 4 == 0 and the columns are even: a float2 is entirely inside or outside the image
+            const bool in_l = (y < H) && (xl >= 0) && (xl < W);
+            const bool in_r = (y < H) && (xl + HALF >= 0) && (xl + HALF < W);
+            float2 dl = make_float2(0.f, 0.f), dr = dl, sl = dl, sr = dl;
+            if (in_l) {
+                dl = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + xl));
+                if (sparse) sl = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + xl));
             }
+            if (in_r) {
+                dr = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + xl + HALF));
+                if (sparse) sr = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + xl + HALF));
+            }
+            d0v[r][0] = make_float2(dl.x, dr.x); d0v[r][1] = make_float2(dl.y, dr.y);
+            d[r][0] = mk(dl.x, dr.x); d[r][1] = mk(dl.y, dr.y);
+            m[r][0] = make_float2(signf(sl.x), signf(sr.x)); m[r][1] = make_float2(signf(sl.y), signf(sr.y));
         }
 
         mbar_wait(bar_tma, ph_tma);
         ph_tma ^= 1;
 
         // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
-        // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box, dx_k is applied here: the thread reads its own
-        // PC columns of plane k and takes the missing neighbour column from the next / previous lane (tile edge
-        // lanes read the apron column of the staged row instead).
+        // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box; dx_k is a plain column offset into the staged
+        // row (whose 4-column apron holds the real neighbours of the tile's edge columns).
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
             const int y = y_thr + r;
-            float S[PC], A[PC];
+            float2 S[PCH], A[PCH], a[8][PCH];
 #pragma unroll
-            for (int j = 0; j < PC; ++j) { S[j] = 0.f; A[j] = 0.f; }
-            float a[8][PC];
+            for (int j = 0; j < PCH; ++j) { S[j] = make_float2(0.f, 0.f); A[j] = S[j]; }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
-                float v[PC];
-                load_row_smem<PC>(row, v);
-                constexpr int kDx[8] = {1, 0, -1, 1, -1, 1, 0, -1};
-                if (kDx[k] == 1) {
-                    float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
-                    if (lane == 31) nb = row[PC];
+                const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PCH + off2_dx(k);
 #pragma unroll
-                    for (int j = 0; j < PC - 1; ++j) a[k][j] = v[j + 1];
-                    a[k][PC - 1] = nb;
-                } else if (kDx[k] == -1) {
-                    float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
-                    if (lane == 0) nb = row[-1];
-#pragma unroll
-                    for (int j = PC - 1; j > 0; --j) a[k][j] = v[j - 1];
-                    a[k][0] = nb;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) a[k][j] = v[j];
-                }
-#pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    if (ABS) a[k][j] = fabsf(a[k][j]);        // cspn.py:88-89
-                    S[j] += fabsf(a[k][j]);                    // cspn.py:135-136
-                    A[j] += a[k][j];                           // numerator of gate_sum, cspn.py:139
+                for (int j = 0; j < PCH; ++j) {
+                    float gl = row[j], gr = row[j + HALF];
+                    if (ABS) { gl = fabsf(gl); gr = fabsf(gr); }           // cspn.py:88-89
+                    a[k][j] = make_float2(gl, gr);
+                    S[j].x += fabsf(gl); S[j].y += fabsf(gr);              // cspn.py:135-136
+                    A[j].x += gl; A[j].y += gr;                            // numerator of gate_sum, cspn.py:139
                 }
             }
+            const bool row_in = y < H;
 #pragma unroll
-            for (int j = 0; j < PC; ++j) {
-                const int x = x_thr + j;
-                const bool in = (y < H) && (x >= 0) && (x < W);
-                const float inv = rcp_approx(S[j]);
-                const float om = 1.f - m[r][j];
-                const float scale = in ? om * inv : 0.f;      // pixels outside the image: w = 0, c = 0, d = 0 forever
-                const float kappa = om * (1.f - A[j] * inv) + m[r][j];
+            for (int j = 0; j < PCH; ++j) {
+                const bool in_l = row_in && (xl + j >= 0) && (xl + j < W);
+                const bool in_r = row_in && (xl + j + HALF >= 0) && (xl + j + HALF < W);
+                const float inv_l = rcp_approx(S[j].x), inv_r = rcp_approx(S[j].y);
+                const float om_l = 1.f - m[r][j].x, om_r = 1.f - m[r][j].y;
+                // pixels outside the image: w = 0, c = 0, d = 0 forever
+                const float2 scale = make_float2(in_l ? om_l * inv_l : 0.f, in_r ? om_r * inv_r : 0.f);
+                const float kap_l = om_l * (1.f - A[j].x * inv_l) + m[r][j].x;
+                const float kap_r = om_r * (1.f - A[j].y * inv_r) + m[r][j].y;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
-                c[r][j] = in ? kappa * d[r][j] : 0.f;
+                for (int k = 0; k < 8; ++k) w[r][j][k] = mk(a[k][j].x * scale.x, a[k][j].y * scale.y);
+                c[r][j] = mk(in_l ? kap_l * d0v[r][j].x : 0.f, in_r ? kap_r * d0v[r][j].y : 0.f);
             }
         }
         __syncthreads();  // every warp is done with the staging buffer
@@ -465,20 +475,24 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 fence_proxy_async();  // generic-proxy reads of `stage` above are ordered before the async-proxy writes
                 issue_stage(next);
             }
-            // its blur / sparse rows: pull the lines into L2
+            // its blur / sparse rows: pull the lines into L2 (one lane per 128-byte line of each half-row)
             const int strip_n = next % prm.n_strips, bc_n = next / prm.n_strips;
-            const int xn = prm.tile_x0[strip_n] + lane * PC;
-            // one lane per 128-byte line of the row segment this warp will read
-            const bool pf_lane = lane == 0 || ((lane - 1) * PC) / 32 != (lane * PC) / 32;
-            if (pf_lane && xn < W) {
+            const int xn = prm.tile_x0[strip_n] + lane * PCH;
+            if ((lane * PCH) % 32 == 0) {
                 const float* bn = prm.blur + (size_t)bc_n * HW;
                 const float* sn = prm.sparse ? prm.sparse + (size_t)(bc_n / prm.C) * HW : nullptr;
 #pragma unroll
                 for (int r = 0; r < PR; ++r) {
                     const int y = y_thr + r;
                     if (y < H) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + xn));
-                        if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + xn));
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int x = xn + h * HALF;
+                            if (x < W) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + x));
+                                if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + x));
+                            }
+                        }
                     }
                 }
             }
@@ -488,13 +502,13 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
         first = false;
         const int iters = prm.iters;
-        publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
-        float d2[PR][PC];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
+        publish<PR, PCH, NW, 0>(xc, wy, d[0], d[PR - 1]);
+        pair_t d2[PR][PCH];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
         for (int it = 0; it < iters; it += 2) {
-            iterate<PR, PC, NW, 0>(xc, wy, ph0, it + 1 == iters, w, c, d, d2);
+            iterate<PR, PCH, NW, 0>(xc, wy, ph0, it + 1 == iters, w, c, d, d2);
             ph0 ^= 1;
             if (it + 1 < iters) {
-                iterate<PR, PC, NW, 1>(xc, wy, ph1, it + 2 == iters, w, c, d2, d);
+                iterate<PR, PCH, NW, 1>(xc, wy, ph1, it + 2 == iters, w, c, d2, d);
                 ph1 ^= 1;
             }
         }
@@ -503,7 +517,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
             for (int r = 0; r < PR; ++r)
 #pragma unroll
-                for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
+                for (int j = 0; j < PCH; ++j) d[r][j] = d2[r][j];
         }
 
         // ---- epilogue: useful columns straight to global ------------------------------------------------
@@ -513,22 +527,10 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         for (int r = 0; r < PR; ++r) {
             const int y = y_thr + r;
             if (y >= H) continue;
-            if constexpr (PC % 4 == 0) {
-#pragma unroll
-                for (int q = 0; q < PC / 4; ++q) {
-                    const int x = x_thr + 4 * q;
-                    if (x >= ux0 && x < ux1)
-                        __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x),
-                               make_float4(d[r][4 * q], d[r][4 * q + 1], d[r][4 * q + 2], d[r][4 * q + 3]));
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < PC / 2; ++q) {
-                    const int x = x_thr + 2 * q;
-                    if (x >= ux0 && x < ux1)
-                        __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + x), make_float2(d[r][2 * q], d[r][2 * q + 1]));
-                }
-            }
+            if (xl >= ux0 && xl < ux1)
+                __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + xl), make_float2(lo(d[r][0]), lo(d[r][1])));
+            if (xl + HALF >= ux0 && xl + HALF < ux1)
+                __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + xl + HALF), make_float2(hi(d[r][0]), hi(d[r][1])));
         }
     }
     // No CTA may exit while a neighbour could still address its shared memory.
@@ -538,28 +540,28 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 // ---- host side: configurations, planner, launch ---------------------------------------------------
 
 struct KernelCfg {
-    int PR, PC, NW;
+    int PR, PCH, NW;
     const void* fn[2];  // [norm_abs]
     size_t smem;
     int RB() const { return PR * NW; }
-    int TW() const { return 32 * PC; }
+    int TW() const { return 64 * PCH; }
 };
 
-template <int PR, int PC, int NW>
+template <int PR, int PCH, int NW>
 KernelCfg make_cfg() {
-    return KernelCfg{PR, PC, NW,
-                     {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true>},
-                     Cfg<PR, PC, NW>::kSmemBytes};
+    return KernelCfg{PR, PCH, NW,
+                     {(const void*)&cspn2d_cluster_kernel<PR, PCH, NW, false>, (const void*)&cspn2d_cluster_kernel<PR, PCH, NW, true>},
+                     Cfg<PR, PCH, NW>::kSmemBytes};
 }
 
-// The menu the planner picks from.  Register budget: 10 registers per pixel of state; PR*PC <= 20 pixels
-// at 256 threads (255 registers), <= 16 at 288-320 threads.
+// The menu the planner picks from.  Register budget: 10 registers per pixel of state (+2 for the second value set);
+// 8 warps (2 per SM sub-partition) may use 255 registers each -> up to 20 pixels per thread.
 const std::vector<KernelCfg>& configs() {
     static const std::vector<KernelCfg> v = {
-        make_cfg<5, 4, 8>(),   // 40 rows x 128 cols, 256 thr, 20 px/thread
-        make_cfg<4, 4, 8>(),   // 32 x 128
-        make_cfg<3, 6, 8>(),   // 24 x 192
-        make_cfg<2, 4, 8>(),   // 16 x 128 (small images)
+        make_cfg<5, 2, 8>(),   // 40 rows x 128 cols, 20 px/thread
+        make_cfg<4, 2, 8>(),   // 32 x 128
+        make_cfg<3, 2, 8>(),   // 24 x 128
+        make_cfg<2, 2, 8>(),   // 16 x 128 (small images)
     };
     return v;
 }
@@ -703,9 +705,9 @@ int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len
     long useful = 0;
     for (int i = 0; i < plan.n_strips; ++i) useful += plan.ux1[i] - plan.ux0[i];
     return snprintf(buf, len,
-                    "cluster: patch %dx%d px/thread, %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
+                    "cluster: patch %d rows x 2x%d cols/thread (FFMA2 pairs), %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
                     "%d strip(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
-                    k.PR, k.PC, k.NW, k.RB(), k.TW(), plan.cs, plan.cs * k.RB(), plan.n_strips, (long)B * C * plan.n_strips,
+                    k.PR, k.PCH, k.NW, k.RB(), k.TW(), plan.cs, plan.cs * k.RB(), plan.n_strips, (long)B * C * plan.n_strips,
                     plan.max_clusters, (double)useful * H / ((double)plan.n_strips * k.TW() * plan.cs * k.RB()), k.smem);
 }
 
