@@ -149,6 +149,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 //                             column tile_x0-4 (TMA needs a 16-byte aligned innermost origin, so the +-1 column
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
 //   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, lane-major pairs)
+//   then cbuf[RB][TW]         folded constant term c' of the current task (lane-major pairs)
 //   then 3 mbarriers          tma, full[0], full[1]
 template <int PR, int PCH, int NW>
 struct Cfg {
@@ -161,7 +162,10 @@ struct Cfg {
     static constexpr size_t kStageBytes = 8 * kPlaneBytes;
     static constexpr size_t kXchParityBytes = (size_t)kSlots * TW * sizeof(float);
     static constexpr size_t kXchBytes = 2 * kXchParityBytes;
-    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + 64;
+    // the folded constant term c' (one float per pixel) lives in shared memory, lane-major like the exchange rows:
+    // it is read once per pixel and iteration (one LDS.128 per patch row), which frees 2*PR registers per thread
+    static constexpr size_t kCBytes = (size_t)RB * TW * sizeof(float);
+    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 64;
     static_assert(PCH == 2, "vectorised global/shared accesses below assume 2 columns per half");
     static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
@@ -250,10 +254,12 @@ __device__ __forceinline__ void load_row_smem(const float* p, pair_t (&v)[2]) {
 __device__ __forceinline__ void store_row_smem(float* p, const pair_t (&v)[2]) {
     *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v[0], v[1]);
 }
-__device__ __forceinline__ void store_row_remote(uint32_t addr, const pair_t (&v)[2], uint32_t bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(addr), "l"(v[0]),
-                 "l"(v[1]), "r"(bar)
-                 : "memory");
+__device__ __forceinline__ void store_row_remote_if(uint32_t addr, const pair_t (&v)[2], uint32_t bar, bool pred) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];\n}\n" ::"r"(addr),
+        "l"(v[0]), "l"(v[1]), "r"(bar), "r"((int)pred)
+        : "memory");
 }
 
 // Per-thread constants of the row exchange.
@@ -264,12 +270,16 @@ struct Xch {
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
     uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's offset, its full[0]
     uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
-    bool has_up, has_dn, signal_lane;
+    bool has_up, has_dn;
+    // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
+    // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
+    bool remote_up, remote_dn, sig_tx, sig;
+    const float* cbuf;    // this thread's first pair of c' (row r is r*TW floats further)
     LaneInfo li;
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
-// halo slots through DSMEM), then signal full[PAR].
+// halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
 template <int PR, int PCH, int NW, int PAR>
 __device__ __forceinline__ void publish(const Xch& x, int wy, const pair_t (&top)[PCH], const pair_t (&bot)[PCH]) {
     using K = Cfg<PR, PCH, NW>;
@@ -277,21 +287,24 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const pair_t (&top
     store_row_smem(p + (1 + 2 * wy) * K::TW, top);
     store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
     const uint32_t bar = x.bar_full0 + 8 * PAR;
-    if (wy == 0 && x.has_up)        // my top row is the "halo from below" (last slot) of the CTA above
-        store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
-    if (wy == NW - 1 && x.has_dn)   // my bottom row is the "halo from above" (slot 0) of the CTA below
-        store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
+    // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
+    store_row_remote_if(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR, x.remote_up);
+    store_row_remote_if(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR, x.remote_dn);
     __syncwarp();
-    if (wy == 0 && x.rx_bytes) mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.signal_lane);
-    else mbar_arrive_if(bar, x.signal_lane);
+    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
+    mbar_arrive_if(bar, x.sig);
 }
 
-// One propagation step d_it (din) -> d_{it+1} (dout); reads exchange buffer PAR, publishes into PAR^1.  Two register
-// sets alternate as input and output, so no value is ever copied between iterations.
-template <int PR, int PCH, int NW, int PAR>
-__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bool last, const pair_t (&w)[PR][PCH][8],
-                                        const pair_t (&c)[PR][PCH], const pair_t (&din)[PR][PCH], pair_t (&dout)[PR][PCH]) {
+// One propagation step d_it (din) -> d_{it+1} (dout); reads exchange buffer PAR, publishes into PAR^1 (not on the
+// last step).  Two register sets alternate as input and output, so no value is ever copied between iterations.
+template <int PR, int PCH, int NW, int PAR, bool PUBLISH>
+__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const pair_t (&w)[PR][PCH][8],
+                                        const pair_t (&din)[PR][PCH], pair_t (&dout)[PR][PCH]) {
     using K = Cfg<PR, PCH, NW>;
+    // c' of the patch: independent of the barrier, so these loads are in flight while we wait
+    pair_t c[PR][PCH];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, c[r]);
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
     // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
     pair_t up[PCH + 2], dn[PCH + 2], e[PR][PCH + 2];
@@ -313,7 +326,7 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, bo
         stencil_row<PCH>(w[0], c[0], up, e[0], e[1], dout[0]);
         stencil_row<PCH>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, dout[PR - 1]);
     }
-    if (!last) publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+    if constexpr (PUBLISH) publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
 #pragma unroll
     for (int r = 1; r <= PR - 2; ++r) stencil_row<PCH>(w[r], c[r], e[r - 1], e[r], e[r + 1], dout[r]);
 }
@@ -326,7 +339,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes);
+    float* cbuf = reinterpret_cast<float*>(smem_raw + K::kStageBytes + K::kXchBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes + K::kCBytes);
     const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
@@ -346,7 +360,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
     xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
     xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
-    xc.signal_lane = lane == 0;
+    xc.remote_up = xc.has_up && wy == 0;
+    xc.remote_dn = xc.has_dn && wy == NW - 1;
+    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
+    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
+    xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * 2 * PCH;
     xc.li.first = lane == 0;
     xc.li.last = lane == 31;
     xc.li.rot_prev = (lane + 31) & 31;
@@ -399,7 +417,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const int xl = tile_x0 + lane * PCH;  // first column of this thread in the left half; right half: + HALF
 
         // ---- thread state: pairs (.x = left-half pixel, .y = right-half pixel) ---------------------------
-        pair_t w[PR][PCH][8], c[PR][PCH], d[PR][PCH];
+        pair_t w[PR][PCH][8], d[PR][PCH];
         float2 d0v[PR][PCH];
         const float* blur = prm.blur + (size_t)bc * HW;
         const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
@@ -436,6 +454,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         for (int r = 0; r < PR; ++r) {
             const int y = y_thr + r;
             float2 S[PCH], A[PCH], a[8][PCH];
+            pair_t cj[PCH];
 #pragma unroll
             for (int j = 0; j < PCH; ++j) { S[j] = make_float2(0.f, 0.f); A[j] = S[j]; }
 #pragma unroll
@@ -463,8 +482,10 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 const float kap_r = om_r * (1.f - A[j].y * inv_r) + m[r][j].y;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) w[r][j][k] = mk(a[k][j].x * scale.x, a[k][j].y * scale.y);
-                c[r][j] = mk(in_l ? kap_l * d0v[r][j].x : 0.f, in_r ? kap_r * d0v[r][j].y : 0.f);
+                cj[j] = mk(in_l ? kap_l * d0v[r][j].x : 0.f, in_r ? kap_r * d0v[r][j].y : 0.f);
             }
+            // only this thread ever reads these values back: no barrier needed
+            store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);
         }
         __syncthreads();  // every warp is done with the staging buffer
 
@@ -504,13 +525,21 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const int iters = prm.iters;
         publish<PR, PCH, NW, 0>(xc, wy, d[0], d[PR - 1]);
         pair_t d2[PR][PCH];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
-        for (int it = 0; it < iters; it += 2) {
-            iterate<PR, PCH, NW, 0>(xc, wy, ph0, it + 1 == iters, w, c, d, d2);
+        int it = 0;
+        for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
+            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, d2);
             ph0 ^= 1;
-            if (it + 1 < iters) {
-                iterate<PR, PCH, NW, 1>(xc, wy, ph1, it + 2 == iters, w, c, d2, d);
-                ph1 ^= 1;
-            }
+            iterate<PR, PCH, NW, 1, true>(xc, wy, ph1, w, d2, d);
+            ph1 ^= 1;
+        }
+        if (iters - it == 2) {              // the last step of a task has nobody to publish to
+            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, d2);
+            ph0 ^= 1;
+            iterate<PR, PCH, NW, 1, false>(xc, wy, ph1, w, d2, d);
+            ph1 ^= 1;
+        } else if (iters - it == 1) {
+            iterate<PR, PCH, NW, 0, false>(xc, wy, ph0, w, d, d2);
+            ph0 ^= 1;
         }
         cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
         if (iters & 1) {
