@@ -207,42 +207,49 @@ struct LaneInfo {
     bool first, last;         // lane 0 / lane 31
 };
 
-// Row of PCH pixel pairs with its two x-neighbour pairs: e[0] = left, e[1..PCH] = own, e[PCH+1] = right.
+// The two x-neighbour pairs of a row of PCH pixel pairs:
 //   left pair  = columns (PCH*l - 1,  TW/2 + PCH*l - 1):  lane l-1's last pair, except for lane 0, whose .x lies
 //                outside the tile (0: image border, or strip halo that decays) and whose .y is column TW/2-1,
 //                i.e. the .x of lane 31's last pair;
 //   right pair = columns (PCH*l + PCH, TW/2 + PCH*l + PCH): lane l+1's first pair, except for lane 31, whose .x is
 //                column TW/2 = the .y of lane 0's first pair and whose .y lies outside the tile.
 template <int PCH>
-__device__ __forceinline__ void extend_row(const pair_t (&v)[PCH], pair_t (&e)[PCH + 2], const LaneInfo& li) {
+__device__ __forceinline__ void row_edges(const pair_t (&v)[PCH], pair_t& left, pair_t& right, const LaneInfo& li) {
     const float ax = lo(v[PCH - 1]), ay = hi(v[PCH - 1]), bx = lo(v[0]), by = hi(v[0]);
     const float lx = __shfl_up_sync(0xffffffffu, ax, 1);
     const float ly = __shfl_sync(0xffffffffu, li.last ? ax : ay, li.rot_prev);
     const float rx = __shfl_sync(0xffffffffu, li.first ? by : bx, li.rot_next);
     const float ry = __shfl_down_sync(0xffffffffu, by, 1);
-    e[0] = mk(li.first ? 0.f : lx, ly);
-    e[PCH + 1] = mk(rx, li.last ? 0.f : ry);
-#pragma unroll
-    for (int j = 0; j < PCH; ++j) e[j + 1] = v[j];
+    left = mk(li.first ? 0.f : lx, ly);
+    right = mk(rx, li.last ? 0.f : ry);
 }
 
-// new value of one row: c + sum_k w_k * neighbour_k ; up = row y-1, cur = row y, dn = row y+1 (extended rows)
+// Extended row view: x(-1) = left edge pair, x(0..PCH-1) = own pairs, x(PCH) = right edge pair.
 template <int PCH>
-__device__ __forceinline__ void stencil_row(const pair_t (&w)[PCH][8], const pair_t (&c)[PCH], const pair_t (&up)[PCH + 2],
-                                            const pair_t (&cur)[PCH + 2], const pair_t (&dn)[PCH + 2], pair_t (&o)[PCH]) {
-#pragma unroll
-    for (int j = 0; j < PCH; ++j) {
-        pair_t acc = c[j];
-        acc = ffma2(w[j][0], dn[j + 2], acc);   // (+1,+1)
-        acc = ffma2(w[j][1], dn[j + 1], acc);   // (+1, 0)
-        acc = ffma2(w[j][2], dn[j], acc);       // (+1,-1)
-        acc = ffma2(w[j][3], cur[j + 2], acc);  // ( 0,+1)
-        acc = ffma2(w[j][4], cur[j], acc);      // ( 0,-1)
-        acc = ffma2(w[j][5], up[j + 2], acc);   // (-1,+1)
-        acc = ffma2(w[j][6], up[j + 1], acc);   // (-1, 0)
-        acc = ffma2(w[j][7], up[j], acc);       // (-1,-1)
-        o[j] = acc;
-    }
+struct Row {
+    const pair_t (&v)[PCH];
+    const pair_t (&ed)[2];
+    __device__ __forceinline__ pair_t x(int j) const { return j < 0 ? ed[0] : (j >= PCH ? ed[1] : v[j]); }
+};
+
+// Taps of the 3x3 stencil grouped by the row they read (channel order of cspn.py, see common.cuh):
+//   row below (dy=+1): k = 0 (dx=+1), 1 (0), 2 (-1);  same row: k = 3 (+1), 4 (-1);  row above (dy=-1): k = 5 (+1), 6 (0), 7 (-1)
+template <int PCH>
+__device__ __forceinline__ pair_t taps_below(const pair_t (&w)[8], const Row<PCH>& r, int j, pair_t acc) {
+    acc = ffma2(w[0], r.x(j + 1), acc);
+    acc = ffma2(w[1], r.x(j), acc);
+    return ffma2(w[2], r.x(j - 1), acc);
+}
+template <int PCH>
+__device__ __forceinline__ pair_t taps_same(const pair_t (&w)[8], const Row<PCH>& r, int j, pair_t acc) {
+    acc = ffma2(w[3], r.x(j + 1), acc);
+    return ffma2(w[4], r.x(j - 1), acc);
+}
+template <int PCH>
+__device__ __forceinline__ pair_t taps_above(const pair_t (&w)[8], const Row<PCH>& r, int j, pair_t acc) {
+    acc = ffma2(w[5], r.x(j + 1), acc);
+    acc = ffma2(w[6], r.x(j), acc);
+    return ffma2(w[7], r.x(j - 1), acc);
 }
 
 // exchange rows are stored lane-major: lane l's PCH pairs are 2*PCH consecutive floats at offset 2*PCH*l
@@ -295,40 +302,63 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const pair_t (&top
     mbar_arrive_if(bar, x.sig);
 }
 
-// One propagation step d_it (din) -> d_{it+1} (dout); reads exchange buffer PAR, publishes into PAR^1 (not on the
-// last step).  Two register sets alternate as input and output, so no value is ever copied between iterations.
+// One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
+// into PAR^1 (not on the last step).  Two register sets alternate as input and output: nothing is copied.
+//
+// Ordering is what makes the exchange free: everything that does not need the neighbours' rows -- all interior rows
+// and 5 of the 8 taps of the two boundary rows -- is issued BEFORE the mbarrier wait; after the wait only the 3 taps
+// that read the row above / below remain, then the new boundary rows are published at once, and the x-edges of the
+// new rows (shuffles) are computed in the tail, off the critical path of the other warps.
 template <int PR, int PCH, int NW, int PAR, bool PUBLISH>
 __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const pair_t (&w)[PR][PCH][8],
-                                        const pair_t (&din)[PR][PCH], pair_t (&dout)[PR][PCH]) {
+                                        const pair_t (&din)[PR][PCH], const pair_t (&ein)[PR][2], pair_t (&dout)[PR][PCH],
+                                        pair_t (&eout)[PR][2]) {
     using K = Cfg<PR, PCH, NW>;
-    // c' of the patch: independent of the barrier, so these loads are in flight while we wait
-    pair_t c[PR][PCH];
+    static_assert(PR >= 2, "a patch needs distinct top and bottom rows");
+    // ---- before the wait -------------------------------------------------------------------------------
+    pair_t top[PCH], bot[PCH];
+    {
+        pair_t c[PCH];
+        load_row_smem(x.cbuf, c);
+        const Row<PCH> r0{din[0], ein[0]}, r1{din[1], ein[1]};
 #pragma unroll
-    for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, c[r]);
+        for (int j = 0; j < PCH; ++j) top[j] = taps_below<PCH>(w[0][j], r1, j, taps_same<PCH>(w[0][j], r0, j, c[j]));
+        load_row_smem(x.cbuf + (PR - 1) * K::TW, c);
+        const Row<PCH> rl{din[PR - 1], ein[PR - 1]}, rp{din[PR - 2], ein[PR - 2]};
+#pragma unroll
+        for (int j = 0; j < PCH; ++j) bot[j] = taps_above<PCH>(w[PR - 1][j], rp, j, taps_same<PCH>(w[PR - 1][j], rl, j, c[j]));
+    }
+#pragma unroll
+    for (int r = 1; r <= PR - 2; ++r) {
+        pair_t c[PCH];
+        load_row_smem(x.cbuf + r * K::TW, c);
+        const Row<PCH> ru{din[r - 1], ein[r - 1]}, rc{din[r], ein[r]}, rd{din[r + 1], ein[r + 1]};
+#pragma unroll
+        for (int j = 0; j < PCH; ++j)
+            dout[r][j] = taps_above<PCH>(w[r][j], ru, j, taps_same<PCH>(w[r][j], rc, j, taps_below<PCH>(w[r][j], rd, j, c[j])));
+    }
+    // ---- the neighbours' rows ----------------------------------------------------------------------------
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
-    // OLD values of every row of the patch with their x-neighbours (shuffles), plus the rows above / below
-    pair_t up[PCH + 2], dn[PCH + 2], e[PR][PCH + 2];
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
-        pair_t t[PCH];
-        load_row_smem(p + (2 * wy) * K::TW, t);        // row above my patch
-        extend_row<PCH>(t, up, x.li);
-        load_row_smem(p + (2 * wy + 3) * K::TW, t);    // row below my patch
-        extend_row<PCH>(t, dn, x.li);
-    }
+        pair_t u[PCH], ue[2], d[PCH], de[2];
+        load_row_smem(p + (2 * wy) * K::TW, u);        // row above my patch
+        load_row_smem(p + (2 * wy + 3) * K::TW, d);    // row below my patch
+        row_edges<PCH>(u, ue[0], ue[1], x.li);
+        row_edges<PCH>(d, de[0], de[1], x.li);
+        const Row<PCH> ru{u, ue}, rd{d, de};
 #pragma unroll
-    for (int r = 0; r < PR; ++r) extend_row<PCH>(din[r], e[r], x.li);
-    // boundary rows first: they go out to the neighbours (shared memory / DSMEM) and the latency of that exchange
-    // hides behind the interior rows computed afterwards
-    if constexpr (PR == 1) {
-        stencil_row<PCH>(w[0], c[0], up, e[0], dn, dout[0]);
-    } else {
-        stencil_row<PCH>(w[0], c[0], up, e[0], e[1], dout[0]);
-        stencil_row<PCH>(w[PR - 1], c[PR - 1], e[PR - 2], e[PR - 1], dn, dout[PR - 1]);
+        for (int j = 0; j < PCH; ++j) {
+            dout[0][j] = taps_above<PCH>(w[0][j], ru, j, top[j]);
+            dout[PR - 1][j] = taps_below<PCH>(w[PR - 1][j], rd, j, bot[j]);
+        }
     }
-    if constexpr (PUBLISH) publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+    if constexpr (PUBLISH) {
+        publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+        // ---- tail: x-edges of the new rows, for the next step ------------------------------------------------
 #pragma unroll
-    for (int r = 1; r <= PR - 2; ++r) stencil_row<PCH>(w[r], c[r], e[r - 1], e[r], e[r + 1], dout[r]);
+        for (int r = 0; r < PR; ++r) row_edges<PCH>(dout[r], eout[r][0], eout[r][1], x.li);
+    }
 }
 
 template <int PR, int PCH, int NW, bool ABS>
@@ -524,21 +554,24 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         first = false;
         const int iters = prm.iters;
         publish<PR, PCH, NW, 0>(xc, wy, d[0], d[PR - 1]);
-        pair_t d2[PR][PCH];  // second register set: d -> d2 on even iterations, d2 -> d on odd ones
+        pair_t e[PR][2];                 // x-edges (left, right pair) of the rows of d
+#pragma unroll
+        for (int r = 0; r < PR; ++r) row_edges<PCH>(d[r], e[r][0], e[r][1], xc.li);
+        pair_t d2[PR][PCH], e2[PR][2];   // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
-            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, d2);
+            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
-            iterate<PR, PCH, NW, 1, true>(xc, wy, ph1, w, d2, d);
+            iterate<PR, PCH, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
-            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, d2);
+            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
-            iterate<PR, PCH, NW, 1, false>(xc, wy, ph1, w, d2, d);
+            iterate<PR, PCH, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         } else if (iters - it == 1) {
-            iterate<PR, PCH, NW, 0, false>(xc, wy, ph0, w, d, d2);
+            iterate<PR, PCH, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
         }
         cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
