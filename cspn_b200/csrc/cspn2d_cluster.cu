@@ -707,10 +707,9 @@ bool make_plan(int B, int C, int H, int W, int iters, int dev, Plan& best, char*
         if (!layout_strips(W, k.TW(), iters, p)) continue;
         const int mac = dev >= 0 ? max_active_clusters(ci, cs, dev) : kProbe256[cs];
         if (mac <= 0) continue;
-        const long tasks = (long)B * C * p.n_strips;
-        const long waves = (tasks + mac - 1) / mac;
-        // per-task time ~ pixels per CTA x (8 FMA/iter + prologue), issue-bound
-        p.cost = (double)waves * k.RB() * k.TW() * (8.0 * iters + 60.0);
+        // Steady-state cost per image: strips x per-task work / co-resident clusters.  Deliberately independent of
+        // B and C, so the same image gets the same tiling (hence bit-identical results) whatever batch it is part of.
+        p.cost = (double)p.n_strips * k.RB() * k.TW() * (8.0 * iters + 60.0) / mac;
         p.cfg = ci; p.cs = cs; p.max_clusters = mac;
         if (best.cfg < 0 || p.cost < best.cost) best = p;
     }
