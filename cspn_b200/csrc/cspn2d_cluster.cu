@@ -28,6 +28,7 @@
 // No tensor cores: a 9-point stencil with per-pixel weights is FMA + HBM bound, not a contraction.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -624,6 +625,7 @@ const std::vector<KernelCfg>& configs() {
         make_cfg<4, 2, 8>(),   // 32 x 128
         make_cfg<3, 2, 8>(),   // 24 x 128
         make_cfg<2, 2, 8>(),   // 16 x 128 (small images)
+        make_cfg<3, 2, 12>(),  // 36 x 128, 12 px/thread, 3 warps per sub-partition (<= 168 registers)
     };
     return v;
 }
@@ -699,7 +701,11 @@ bool make_plan(int B, int C, int H, int W, int iters, int dev, Plan& best, char*
     static const int kProbe256[17] = {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7};
     best.cfg = -1;
     const auto& cf = configs();
+    // developer hook for tuning runs: CSPN_B200_FORCE_CFG=<index into configs()>
+    const char* force = getenv("CSPN_B200_FORCE_CFG");
+    const int forced = force ? atoi(force) : -1;
     for (int ci = 0; ci < (int)cf.size(); ++ci) {
+        if (forced >= 0 && ci != forced) continue;
         const KernelCfg& k = cf[ci];
         const int cs = (H + k.RB() - 1) / k.RB();
         if (cs > 16) continue;
