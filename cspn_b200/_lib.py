@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, '_build', 'libcspn_b200.so')
+LIB_PATH = os.environ.get('CSPN_B200_LIB') or os.path.join(HERE, '_build', 'libcspn_b200.so')   # env: developer hook for tuning builds
 
 OK = 0
 ALGO_AUTO, ALGO_GENERIC, ALGO_CLUSTER = 0, 1, 2

@@ -198,6 +198,9 @@ __device__ __forceinline__ float hi(pair_t p) {
     return y;
 }
 __device__ __forceinline__ pair_t ffma2(pair_t a, pair_t b, pair_t c) {
+#ifdef CSPN_ABLATE_NO_FMA    // timing experiment only: wrong results
+    return a ^ b ^ c;
+#endif
     pair_t r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
@@ -216,6 +219,9 @@ struct LaneInfo {
 //                column TW/2 = the .y of lane 0's first pair and whose .y lies outside the tile.
 template <int PCH>
 __device__ __forceinline__ void row_edges(const pair_t (&v)[PCH], pair_t& left, pair_t& right, const LaneInfo& li) {
+#ifdef CSPN_ABLATE_NO_SHFL   // timing experiment only: wrong results
+    left = v[PCH - 1]; right = v[0]; return;
+#endif
     const float ax = lo(v[PCH - 1]), ay = hi(v[PCH - 1]), bx = lo(v[0]), by = hi(v[0]);
     const float lx = __shfl_up_sync(0xffffffffu, ax, 1);
     const float ly = __shfl_sync(0xffffffffu, li.last ? ax : ay, li.rot_prev);
@@ -255,6 +261,9 @@ __device__ __forceinline__ pair_t taps_above(const pair_t (&w)[8], const Row<PCH
 
 // exchange rows are stored lane-major: lane l's PCH pairs are 2*PCH consecutive floats at offset 2*PCH*l
 __device__ __forceinline__ void load_row_smem(const float* p, pair_t (&v)[2]) {
+#ifdef CSPN_ABLATE_NO_LDS    // timing experiment only: wrong results
+    v[0] = (pair_t)(size_t)p; v[1] = v[0] + 1; return;
+#endif
     const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
     v[0] = t.x;
     v[1] = t.y;
@@ -337,6 +346,8 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
 #pragma unroll
         for (int j = 0; j < PCH; ++j)
             dout[r][j] = taps_above<PCH>(w[r][j], ru, j, taps_same<PCH>(w[r][j], rc, j, taps_below<PCH>(w[r][j], rd, j, c[j])));
+        // x-edges of the finished interior row right away: shuffle/select work interleaves with the FMA-heavy part
+        if constexpr (PUBLISH) row_edges<PCH>(dout[r], eout[r][0], eout[r][1], x.li);
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
@@ -356,9 +367,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
     if constexpr (PUBLISH) {
         publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
-        // ---- tail: x-edges of the new rows, for the next step ------------------------------------------------
-#pragma unroll
-        for (int r = 0; r < PR; ++r) row_edges<PCH>(dout[r], eout[r][0], eout[r][1], x.li);
+        // ---- tail: x-edges of the two new boundary rows, for the next step -----------------------------------
+        row_edges<PCH>(dout[0], eout[0][0], eout[0][1], x.li);
+        row_edges<PCH>(dout[PR - 1], eout[PR - 1][0], eout[PR - 1][1], x.li);
     }
 }
 
