@@ -138,38 +138,38 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
-// Thread patch and the FFMA2 pairing.  A tile is TW = 64*PCH columns wide.  Lane l owns, in each of its PR rows,
-// PCH columns of the LEFT half (PCH*l + j) and the PCH columns at the same offset in the RIGHT half
-// (TW/2 + PCH*l + j).  Pixel j of the left half and pixel j of the right half are kept together as one float2
-// (.x = left, .y = right): every stencil tap then reads an aligned register pair again, so the 8 FMAs of two
-// pixels issue as 8 FFMA2 (fma.rn.f32x2, new on sm_100) -- half the issue slots of scalar FFMA, which is what
-// bounds this kernel (FP32 pipe, not HBM, at 24 iterations).
-//
 // Shared memory map (dynamic):
 //   [0, 8*RB*TWP*4)           stage: 8 guidance planes [k][RB][TWP], TWP = TW + 8: the box of channel k starts at
 //                             column tile_x0-4 (TMA needs a 16-byte aligned innermost origin, so the +-1 column
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
-//   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, lane-major pairs)
-//   then cbuf[RB][TW]         folded constant term c' of the current task (lane-major pairs)
+//   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
+//   then cbuf[RB][TW]         folded constant term c' of the current task
 //   then 3 mbarriers          tma, full[0], full[1]
-template <int PR, int PCH, int NW>
+//
+// Arithmetic is scalar FFMA on purpose.  fma.rn.f32x2 (FFMA2, new on sm_100) was tried with pixel pairs in 64-bit
+// registers: with 160 weight registers live per thread it sustains only ~0.22 FFMA2/clk per sub-partition (715 cycles
+// for one 20-pixel step of two warps) against 489-550 cycles for the same step in scalar FFMA
+// (profiles/r01_stencil_probe_ffma_vs_ffma2.txt): three distinct 64-bit register operands per instruction starve on
+// register-file bandwidth.
+template <int PR, int PC, int NW>
 struct Cfg {
     static constexpr int kThreads = 32 * NW;
-    static constexpr int RB = NW * PR;    // rows per CTA band
-    static constexpr int TW = 64 * PCH;   // tile (strip) width
-    static constexpr int TWP = TW + 8;    // staged row pitch: 4 apron columns on each side
+    static constexpr int RB = NW * PR;   // rows per CTA band
+    static constexpr int TW = 32 * PC;   // tile (strip) width
+    static constexpr int TWP = TW + 8;   // staged row pitch: 4 apron columns on each side
     static constexpr int kSlots = 2 * NW + 2;
     static constexpr size_t kPlaneBytes = (size_t)RB * TWP * sizeof(float);
     static constexpr size_t kStageBytes = 8 * kPlaneBytes;
     static constexpr size_t kXchParityBytes = (size_t)kSlots * TW * sizeof(float);
     static constexpr size_t kXchBytes = 2 * kXchParityBytes;
-    // the folded constant term c' (one float per pixel) lives in shared memory, lane-major like the exchange rows:
-    // it is read once per pixel and iteration (one LDS.128 per patch row), which frees 2*PR registers per thread
+    // the folded constant term c' (one float per pixel) lives in shared memory: it is read once per pixel and
+    // iteration (one LDS.128 per patch row), which frees PR*PC registers per thread
     static constexpr size_t kCBytes = (size_t)RB * TW * sizeof(float);
     static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 64;
-    static_assert(PCH == 2, "vectorised global/shared accesses below assume 2 columns per half");
+    static_assert(PC == 4, "vectorised global/shared accesses below assume 4 columns per thread");
     static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
+    static_assert(PR >= 2, "a patch needs distinct top and bottom rows");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 };
 
@@ -179,127 +179,84 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// A pixel pair lives in ONE 64-bit register (an aligned register pair) from the moment it is produced by FFMA2 until
-// it is consumed; halves are only named when a shuffle or a select needs a 32-bit value.
-typedef unsigned long long pair_t;
-__device__ __forceinline__ pair_t mk(float x, float y) {
-    pair_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
-    return r;
-}
-__device__ __forceinline__ float lo(pair_t p) {
-    float x, y;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p));
-    return x;
-}
-__device__ __forceinline__ float hi(pair_t p) {
-    float x, y;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p));
-    return y;
-}
-__device__ __forceinline__ pair_t ffma2(pair_t a, pair_t b, pair_t c) {
-#ifdef CSPN_ABLATE_NO_FMA    // timing experiment only: wrong results
-    return a ^ b ^ c;
-#endif
-    pair_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
+// The two x-neighbours of a row of PC pixels: the last pixel of lane l-1 and the first of lane l+1.  Outside the tile
+// the neighbour is 0: either the image border (zero padding) or strip halo that decays.
+template <int PC>
+__device__ __forceinline__ void row_edges(const float (&v)[PC], float (&ed)[2], bool first_lane, bool last_lane) {
+    const float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+    const float r = __shfl_down_sync(0xffffffffu, v[0], 1);
+    ed[0] = first_lane ? 0.f : l;
+    ed[1] = last_lane ? 0.f : r;
 }
 
-struct LaneInfo {
-    int rot_prev, rot_next;   // (lane-1)&31, (lane+1)&31
-    bool first, last;         // lane 0 / lane 31
-};
-
-// The two x-neighbour pairs of a row of PCH pixel pairs:
-//   left pair  = columns (PCH*l - 1,  TW/2 + PCH*l - 1):  lane l-1's last pair, except for lane 0, whose .x lies
-//                outside the tile (0: image border, or strip halo that decays) and whose .y is column TW/2-1,
-//                i.e. the .x of lane 31's last pair;
-//   right pair = columns (PCH*l + PCH, TW/2 + PCH*l + PCH): lane l+1's first pair, except for lane 31, whose .x is
-//                column TW/2 = the .y of lane 0's first pair and whose .y lies outside the tile.
-template <int PCH>
-__device__ __forceinline__ void row_edges(const pair_t (&v)[PCH], pair_t& left, pair_t& right, const LaneInfo& li) {
-#ifdef CSPN_ABLATE_NO_SHFL   // timing experiment only: wrong results
-    left = v[PCH - 1]; right = v[0]; return;
-#endif
-    const float ax = lo(v[PCH - 1]), ay = hi(v[PCH - 1]), bx = lo(v[0]), by = hi(v[0]);
-    const float lx = __shfl_up_sync(0xffffffffu, ax, 1);
-    const float ly = __shfl_sync(0xffffffffu, li.last ? ax : ay, li.rot_prev);
-    const float rx = __shfl_sync(0xffffffffu, li.first ? by : bx, li.rot_next);
-    const float ry = __shfl_down_sync(0xffffffffu, by, 1);
-    left = mk(li.first ? 0.f : lx, ly);
-    right = mk(rx, li.last ? 0.f : ry);
-}
-
-// Extended row view: x(-1) = left edge pair, x(0..PCH-1) = own pairs, x(PCH) = right edge pair.
-template <int PCH>
+// Extended row view: (-1) = left neighbour, (0..PC-1) = own pixels, (PC) = right neighbour.
+template <int PC>
 struct Row {
-    const pair_t (&v)[PCH];
-    const pair_t (&ed)[2];
-    __device__ __forceinline__ pair_t x(int j) const { return j < 0 ? ed[0] : (j >= PCH ? ed[1] : v[j]); }
+    const float (&v)[PC];
+    const float (&ed)[2];
+    __device__ __forceinline__ float operator()(int j) const { return j < 0 ? ed[0] : (j >= PC ? ed[1] : v[j]); }
 };
 
-// Taps of the 3x3 stencil grouped by the row they read (channel order of cspn.py, see common.cuh):
-//   row below (dy=+1): k = 0 (dx=+1), 1 (0), 2 (-1);  same row: k = 3 (+1), 4 (-1);  row above (dy=-1): k = 5 (+1), 6 (0), 7 (-1)
-template <int PCH>
-__device__ __forceinline__ pair_t taps_below(const pair_t (&w)[8], const Row<PCH>& r, int j, pair_t acc) {
-    acc = ffma2(w[0], r.x(j + 1), acc);
-    acc = ffma2(w[1], r.x(j), acc);
-    return ffma2(w[2], r.x(j - 1), acc);
-}
-template <int PCH>
-__device__ __forceinline__ pair_t taps_same(const pair_t (&w)[8], const Row<PCH>& r, int j, pair_t acc) {
-    acc = ffma2(w[3], r.x(j + 1), acc);
-    return ffma2(w[4], r.x(j - 1), acc);
-}
-template <int PCH>
-__device__ __forceinline__ pair_t taps_above(const pair_t (&w)[8], const Row<PCH>& r, int j, pair_t acc) {
-    acc = ffma2(w[5], r.x(j + 1), acc);
-    acc = ffma2(w[6], r.x(j), acc);
-    return ffma2(w[7], r.x(j - 1), acc);
+// Channel of the tap that reads the pixel at offset (dy, dx) (channel order of cspn.py, see common.cuh):
+//   (+1,+1)=0 (+1,0)=1 (+1,-1)=2 (0,+1)=3 (0,-1)=4 (-1,+1)=5 (-1,0)=6 (-1,-1)=7
+__host__ __device__ constexpr int tap_of(int dy, int dx) { return dy == 1 ? 1 - dx : (dy == 0 ? (dx == 1 ? 3 : 4) : 6 - dx); }
+
+// Scatter one source row into the accumulators of one destination row.  `src(jx)`, jx = -1..PC, is the extended
+// source row; it sits SRC_DY rows below the destination row whose weights are `w` (+1: the row below, 0: the same
+// row, -1: the row above).  The loop nest is SOURCE-major: the FMAs that consume one source value are adjacent and
+// write different accumulators, so none depends on its predecessor and the shared operand can come from the
+// operand-reuse cache (three distinct register operands per FFMA run at ~2/3 rate on the register file).
+template <int PC, int SRC_DY, typename Src>
+__device__ __forceinline__ void scatter_row(const float (&w)[PC][8], const Src& src, float (&acc)[PC]) {
+#pragma unroll
+    for (int jx = -1; jx <= PC; ++jx) {
+        const float xv = src(jx);
+#pragma unroll
+        for (int dx = 1; dx >= -1; --dx) {
+            const int j = jx - dx;                       // destination column that reads this source with offset dx
+            if (j < 0 || j >= PC) continue;
+            if (SRC_DY == 0 && dx == 0) continue;         // no centre tap
+            acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]);
+        }
+    }
 }
 
-// exchange rows are stored lane-major: lane l's PCH pairs are 2*PCH consecutive floats at offset 2*PCH*l
-__device__ __forceinline__ void load_row_smem(const float* p, pair_t (&v)[2]) {
-#ifdef CSPN_ABLATE_NO_LDS    // timing experiment only: wrong results
-    v[0] = (pair_t)(size_t)p; v[1] = v[0] + 1; return;
-#endif
-    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
-    v[0] = t.x;
-    v[1] = t.y;
+__device__ __forceinline__ void load_row_smem(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
-__device__ __forceinline__ void store_row_smem(float* p, const pair_t (&v)[2]) {
-    *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v[0], v[1]);
+__device__ __forceinline__ void store_row_smem(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
-__device__ __forceinline__ void store_row_remote_if(uint32_t addr, const pair_t (&v)[2], uint32_t bar, bool pred) {
+__device__ __forceinline__ void store_row_remote_if(uint32_t addr, const float (&v)[4], uint32_t bar, bool pred) {
     asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];\n}\n" ::"r"(addr),
-        "l"(v[0]), "l"(v[1]), "r"(bar), "r"((int)pred)
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
+        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n}\n" ::"r"(addr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar), "r"((int)pred)
         : "memory");
 }
 
 // Per-thread constants of the row exchange.
 struct Xch {
-    float* base;          // xch + lane's pair offset (parity 0, slot 0)
+    float* base;          // xch + lane*PC (parity 0, slot 0)
     uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
     uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
-    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's offset, its full[0]
+    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
     uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
     bool has_up, has_dn;
     // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
     // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
     bool remote_up, remote_dn, sig_tx, sig;
-    const float* cbuf;    // this thread's first pair of c' (row r is r*TW floats further)
-    LaneInfo li;
+    bool first_lane, last_lane;
+    const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
 // halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
-template <int PR, int PCH, int NW, int PAR>
-__device__ __forceinline__ void publish(const Xch& x, int wy, const pair_t (&top)[PCH], const pair_t (&bot)[PCH]) {
-    using K = Cfg<PR, PCH, NW>;
+template <int PR, int PC, int NW, int PAR>
+__device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
+    using K = Cfg<PR, PC, NW>;
     float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
     store_row_smem(p + (1 + 2 * wy) * K::TW, top);
     store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
@@ -315,69 +272,50 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const pair_t (&top
 // One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
 // into PAR^1 (not on the last step).  Two register sets alternate as input and output: nothing is copied.
 //
-// Ordering is what makes the exchange free: everything that does not need the neighbours' rows -- all interior rows
-// and 5 of the 8 taps of the two boundary rows -- is issued BEFORE the mbarrier wait; after the wait only the 3 taps
-// that read the row above / below remain, then the new boundary rows are published at once, and the x-edges of the
-// new rows (shuffles) are computed in the tail, off the critical path of the other warps.
-template <int PR, int PCH, int NW, int PAR, bool PUBLISH>
-__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const pair_t (&w)[PR][PCH][8],
-                                        const pair_t (&din)[PR][PCH], const pair_t (&ein)[PR][2], pair_t (&dout)[PR][PCH],
-                                        pair_t (&eout)[PR][2]) {
-    using K = Cfg<PR, PCH, NW>;
-    static_assert(PR >= 2, "a patch needs distinct top and bottom rows");
-    // ---- before the wait -------------------------------------------------------------------------------
-    pair_t top[PCH], bot[PCH];
-    {
-        pair_t c[PCH];
-        load_row_smem(x.cbuf, c);
-        const Row<PCH> r0{din[0], ein[0]}, r1{din[1], ein[1]};
+// Ordering is what makes the exchange free: every source row the thread owns is scattered into the accumulators
+// BEFORE the mbarrier wait; after the wait only the rows above / below the patch remain (3 taps of the two boundary
+// rows), then the new boundary rows are published at once and the x-edges of the new rows (shuffles) are computed in
+// the tail, off the critical path of the other warps.
+template <int PR, int PC, int NW, int PAR, bool PUBLISH>
+__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
+                                        const float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
+                                        float (&eout)[PR][2]) {
+    using K = Cfg<PR, PC, NW>;
+    // ---- before the wait: accumulators start from c', then every own source row is scattered ----------------
 #pragma unroll
-        for (int j = 0; j < PCH; ++j) top[j] = taps_below<PCH>(w[0][j], r1, j, taps_same<PCH>(w[0][j], r0, j, c[j]));
-        load_row_smem(x.cbuf + (PR - 1) * K::TW, c);
-        const Row<PCH> rl{din[PR - 1], ein[PR - 1]}, rp{din[PR - 2], ein[PR - 2]};
+    for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
 #pragma unroll
-        for (int j = 0; j < PCH; ++j) bot[j] = taps_above<PCH>(w[PR - 1][j], rp, j, taps_same<PCH>(w[PR - 1][j], rl, j, c[j]));
-    }
-#pragma unroll
-    for (int r = 1; r <= PR - 2; ++r) {
-        pair_t c[PCH];
-        load_row_smem(x.cbuf + r * K::TW, c);
-        const Row<PCH> ru{din[r - 1], ein[r - 1]}, rc{din[r], ein[r]}, rd{din[r + 1], ein[r + 1]};
-#pragma unroll
-        for (int j = 0; j < PCH; ++j)
-            dout[r][j] = taps_above<PCH>(w[r][j], ru, j, taps_same<PCH>(w[r][j], rc, j, taps_below<PCH>(w[r][j], rd, j, c[j])));
-        // x-edges of the finished interior row right away: shuffle/select work interleaves with the FMA-heavy part
-        if constexpr (PUBLISH) row_edges<PCH>(dout[r], eout[r][0], eout[r][1], x.li);
+    for (int rs = 0; rs < PR; ++rs) {
+        const Row<PC> src{din[rs], ein[rs]};
+        if (rs >= 1) scatter_row<PC, +1>(w[rs - 1], src, dout[rs - 1]);      // source is the row below row rs-1
+        scatter_row<PC, 0>(w[rs], src, dout[rs]);
+        if (rs + 1 < PR) scatter_row<PC, -1>(w[rs + 1], src, dout[rs + 1]);  // source is the row above row rs+1
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
-        pair_t u[PCH], ue[2], d[PCH], de[2];
+        float u[PC], ue[2], d[PC], de[2];
         load_row_smem(p + (2 * wy) * K::TW, u);        // row above my patch
         load_row_smem(p + (2 * wy + 3) * K::TW, d);    // row below my patch
-        row_edges<PCH>(u, ue[0], ue[1], x.li);
-        row_edges<PCH>(d, de[0], de[1], x.li);
-        const Row<PCH> ru{u, ue}, rd{d, de};
-#pragma unroll
-        for (int j = 0; j < PCH; ++j) {
-            dout[0][j] = taps_above<PCH>(w[0][j], ru, j, top[j]);
-            dout[PR - 1][j] = taps_below<PCH>(w[PR - 1][j], rd, j, bot[j]);
-        }
+        row_edges<PC>(u, ue, x.first_lane, x.last_lane);
+        row_edges<PC>(d, de, x.first_lane, x.last_lane);
+        scatter_row<PC, -1>(w[0], Row<PC>{u, ue}, dout[0]);
+        scatter_row<PC, +1>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1]);
     }
     if constexpr (PUBLISH) {
-        publish<PR, PCH, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
-        // ---- tail: x-edges of the two new boundary rows, for the next step -----------------------------------
-        row_edges<PCH>(dout[0], eout[0][0], eout[0][1], x.li);
-        row_edges<PCH>(dout[PR - 1], eout[PR - 1][0], eout[PR - 1][1], x.li);
+        publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+        // ---- tail: x-edges of the new rows, for the next step ------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
     }
 }
 
-template <int PR, int PCH, int NW, bool ABS>
+template <int PR, int PC, int NW, bool ABS>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
-    using K = Cfg<PR, PCH, NW>;
-    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP, HALF = TW / 2;
+    using K = Cfg<PR, PC, NW>;
+    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
@@ -393,7 +331,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const size_t HW = (size_t)H * W;
 
     Xch xc;
-    xc.base = xch + lane * 2 * PCH;
+    xc.base = xch + lane * PC;
     xc.bar_full0 = bar_full0;
     xc.has_up = crank > 0;
     xc.has_dn = crank + 1 < csize;
@@ -406,11 +344,9 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.remote_dn = xc.has_dn && wy == NW - 1;
     xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
     xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
-    xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * 2 * PCH;
-    xc.li.first = lane == 0;
-    xc.li.last = lane == 31;
-    xc.li.rot_prev = (lane + 31) & 31;
-    xc.li.rot_next = (lane + 1) & 31;
+    xc.first_lane = lane == 0;
+    xc.last_lane = lane == 31;
+    xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -456,75 +392,81 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const int bc = task / prm.n_strips;  // b*C + c
         const int b = bc / prm.C;
         const int tile_x0 = prm.tile_x0[strip];
-        const int xl = tile_x0 + lane * PCH;  // first column of this thread in the left half; right half: + HALF
+        const int x_thr = tile_x0 + lane * PC;  // first column of this thread
 
-        // ---- thread state: pairs (.x = left-half pixel, .y = right-half pixel) ---------------------------
-        pair_t w[PR][PCH][8], d[PR][PCH];
-        float2 d0v[PR][PCH];
+        // ---- thread state ---------------------------------------------------------------------------
+        float w[PR][PC][8], d[PR][PC];
         const float* blur = prm.blur + (size_t)bc * HW;
         const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
 
-        // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2)
-        float2 m[PR][PCH];
+        // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2).
+        // W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
+        const bool col_in = (x_thr >= 0) && (x_thr < W);
+        float m[PR][PC];
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
             const int y = y_thr + r;
-            // W % 4 == 0 and the columns are even: a float2 is entirely inside or outside the image
-            const bool in_l = (y < H) && (xl >= 0) && (xl < W);
-            const bool in_r = (y < H) && (xl + HALF >= 0) && (xl + HALF < W);
-            float2 dl = make_float2(0.f, 0.f), dr = dl, sl = dl, sr = dl;
-            if (in_l) {
-                dl = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + xl));
-                if (sparse) sl = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + xl));
+            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), sv = dv;
+            if (col_in && y < H) {
+                dv = __ldg(reinterpret_cast<const float4*>(blur + (size_t)y * W + x_thr));
+                if (sparse) sv = __ldg(reinterpret_cast<const float4*>(sparse + (size_t)y * W + x_thr));
             }
-            if (in_r) {
-                dr = __ldg(reinterpret_cast<const float2*>(blur + (size_t)y * W + xl + HALF));
-                if (sparse) sr = __ldg(reinterpret_cast<const float2*>(sparse + (size_t)y * W + xl + HALF));
-            }
-            d0v[r][0] = make_float2(dl.x, dr.x); d0v[r][1] = make_float2(dl.y, dr.y);
-            d[r][0] = mk(dl.x, dr.x); d[r][1] = mk(dl.y, dr.y);
-            m[r][0] = make_float2(signf(sl.x), signf(sr.x)); m[r][1] = make_float2(signf(sl.y), signf(sr.y));
+            d[r][0] = dv.x; d[r][1] = dv.y; d[r][2] = dv.z; d[r][3] = dv.w;
+            m[r][0] = signf(sv.x); m[r][1] = signf(sv.y); m[r][2] = signf(sv.z); m[r][3] = signf(sv.w);
         }
 
         mbar_wait(bar_tma, ph_tma);
         ph_tma ^= 1;
 
         // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
-        // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box; dx_k is a plain column offset into the staged
-        // row (whose 4-column apron holds the real neighbours of the tile's edge columns).
+        // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box, dx_k is applied here: the thread reads its own
+        // PC columns of plane k and takes the missing neighbour column from the next / previous lane (tile edge
+        // lanes read the apron column of the staged row instead).
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
             const int y = y_thr + r;
-            float2 S[PCH], A[PCH], a[8][PCH];
-            pair_t cj[PCH];
+            float S[PC], A[PC], a[8][PC];
 #pragma unroll
-            for (int j = 0; j < PCH; ++j) { S[j] = make_float2(0.f, 0.f); A[j] = S[j]; }
+            for (int j = 0; j < PC; ++j) { S[j] = 0.f; A[j] = 0.f; }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PCH + off2_dx(k);
+                const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
+                float v[PC];
+                load_row_smem(row, v);
+                if (off2_dx(k) == 1) {
+                    float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+                    if (lane == 31) nb = row[PC];
 #pragma unroll
-                for (int j = 0; j < PCH; ++j) {
-                    float gl = row[j], gr = row[j + HALF];
-                    if (ABS) { gl = fabsf(gl); gr = fabsf(gr); }           // cspn.py:88-89
-                    a[k][j] = make_float2(gl, gr);
-                    S[j].x += fabsf(gl); S[j].y += fabsf(gr);              // cspn.py:135-136
-                    A[j].x += gl; A[j].y += gr;                            // numerator of gate_sum, cspn.py:139
+                    for (int j = 0; j < PC - 1; ++j) a[k][j] = v[j + 1];
+                    a[k][PC - 1] = nb;
+                } else if (off2_dx(k) == -1) {
+                    float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+                    if (lane == 0) nb = row[-1];
+#pragma unroll
+                    for (int j = PC - 1; j > 0; --j) a[k][j] = v[j - 1];
+                    a[k][0] = nb;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) a[k][j] = v[j];
+                }
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    if (ABS) a[k][j] = fabsf(a[k][j]);        // cspn.py:88-89
+                    S[j] += fabsf(a[k][j]);                    // cspn.py:135-136
+                    A[j] += a[k][j];                           // numerator of gate_sum, cspn.py:139
                 }
             }
-            const bool row_in = y < H;
+            float cj[PC];
 #pragma unroll
-            for (int j = 0; j < PCH; ++j) {
-                const bool in_l = row_in && (xl + j >= 0) && (xl + j < W);
-                const bool in_r = row_in && (xl + j + HALF >= 0) && (xl + j + HALF < W);
-                const float inv_l = rcp_approx(S[j].x), inv_r = rcp_approx(S[j].y);
-                const float om_l = 1.f - m[r][j].x, om_r = 1.f - m[r][j].y;
-                // pixels outside the image: w = 0, c = 0, d = 0 forever
-                const float2 scale = make_float2(in_l ? om_l * inv_l : 0.f, in_r ? om_r * inv_r : 0.f);
-                const float kap_l = om_l * (1.f - A[j].x * inv_l) + m[r][j].x;
-                const float kap_r = om_r * (1.f - A[j].y * inv_r) + m[r][j].y;
+            for (int j = 0; j < PC; ++j) {
+                const bool in = col_in && (y < H);
+                const float inv = rcp_approx(S[j]);
+                const float om = 1.f - m[r][j];
+                const float scale = in ? om * inv : 0.f;      // pixels outside the image: w = 0, c = 0, d = 0 forever
+                const float kappa = om * (1.f - A[j] * inv) + m[r][j];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[r][j][k] = mk(a[k][j].x * scale.x, a[k][j].y * scale.y);
-                cj[j] = mk(in_l ? kap_l * d0v[r][j].x : 0.f, in_r ? kap_r * d0v[r][j].y : 0.f);
+                for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
+                cj[j] = in ? kappa * d[r][j] : 0.f;
             }
             // only this thread ever reads these values back: no barrier needed
             store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);
@@ -538,24 +480,18 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 fence_proxy_async();  // generic-proxy reads of `stage` above are ordered before the async-proxy writes
                 issue_stage(next);
             }
-            // its blur / sparse rows: pull the lines into L2 (one lane per 128-byte line of each half-row)
+            // its blur / sparse rows: pull the lines into L2 (one lane per 128-byte line of the row segment)
             const int strip_n = next % prm.n_strips, bc_n = next / prm.n_strips;
-            const int xn = prm.tile_x0[strip_n] + lane * PCH;
-            if ((lane * PCH) % 32 == 0) {
+            const int xn = prm.tile_x0[strip_n] + lane * PC;
+            if ((lane * PC) % 32 == 0 && xn < W) {
                 const float* bn = prm.blur + (size_t)bc_n * HW;
                 const float* sn = prm.sparse ? prm.sparse + (size_t)(bc_n / prm.C) * HW : nullptr;
 #pragma unroll
                 for (int r = 0; r < PR; ++r) {
                     const int y = y_thr + r;
                     if (y < H) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int x = xn + h * HALF;
-                            if (x < W) {
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + x));
-                                if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + x));
-                            }
-                        }
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + xn));
+                        if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + xn));
                     }
                 }
             }
@@ -565,25 +501,25 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
         first = false;
         const int iters = prm.iters;
-        publish<PR, PCH, NW, 0>(xc, wy, d[0], d[PR - 1]);
-        pair_t e[PR][2];                 // x-edges (left, right pair) of the rows of d
+        publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+        float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
-        for (int r = 0; r < PR; ++r) row_edges<PCH>(d[r], e[r][0], e[r][1], xc.li);
-        pair_t d2[PR][PCH], e2[PR][2];   // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
+        for (int r = 0; r < PR; ++r) row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
+        float d2[PR][PC], e2[PR][2];    // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
-            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
-            iterate<PR, PCH, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
+            iterate<PR, PC, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
-            iterate<PR, PCH, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
-            iterate<PR, PCH, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
+            iterate<PR, PC, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         } else if (iters - it == 1) {
-            iterate<PR, PCH, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
+            iterate<PR, PC, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
         }
         cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
@@ -591,20 +527,19 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
             for (int r = 0; r < PR; ++r)
 #pragma unroll
-                for (int j = 0; j < PCH; ++j) d[r][j] = d2[r][j];
+                for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
         }
 
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
         const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
+        if (x_thr >= ux0 && x_thr < ux1) {
 #pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            const int y = y_thr + r;
-            if (y >= H) continue;
-            if (xl >= ux0 && xl < ux1)
-                __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + xl), make_float2(lo(d[r][0]), lo(d[r][1])));
-            if (xl + HALF >= ux0 && xl + HALF < ux1)
-                __stcs(reinterpret_cast<float2*>(out + (size_t)y * W + xl + HALF), make_float2(hi(d[r][0]), hi(d[r][1])));
+            for (int r = 0; r < PR; ++r) {
+                const int y = y_thr + r;
+                if (y < H)
+                    __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x_thr), make_float4(d[r][0], d[r][1], d[r][2], d[r][3]));
+            }
         }
     }
     // No CTA may exit while a neighbour could still address its shared memory.
@@ -614,29 +549,28 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 // ---- host side: configurations, planner, launch ---------------------------------------------------
 
 struct KernelCfg {
-    int PR, PCH, NW;
+    int PR, PC, NW;
     const void* fn[2];  // [norm_abs]
     size_t smem;
     int RB() const { return PR * NW; }
-    int TW() const { return 64 * PCH; }
+    int TW() const { return 32 * PC; }
 };
 
-template <int PR, int PCH, int NW>
+template <int PR, int PC, int NW>
 KernelCfg make_cfg() {
-    return KernelCfg{PR, PCH, NW,
-                     {(const void*)&cspn2d_cluster_kernel<PR, PCH, NW, false>, (const void*)&cspn2d_cluster_kernel<PR, PCH, NW, true>},
-                     Cfg<PR, PCH, NW>::kSmemBytes};
+    return KernelCfg{PR, PC, NW,
+                     {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true>},
+                     Cfg<PR, PC, NW>::kSmemBytes};
 }
 
-// The menu the planner picks from.  Register budget: 10 registers per pixel of state (+2 for the second value set);
-// 8 warps (2 per SM sub-partition) may use 255 registers each -> up to 20 pixels per thread.
+// The menu the planner picks from.  Register budget per pixel: 8 weights + value + second value set (c' is in shared
+// memory); 8 warps (2 per SM sub-partition) may use 255 registers each -> up to 20 pixels per thread.
 const std::vector<KernelCfg>& configs() {
     static const std::vector<KernelCfg> v = {
-        make_cfg<5, 2, 8>(),   // 40 rows x 128 cols, 20 px/thread
-        make_cfg<4, 2, 8>(),   // 32 x 128
-        make_cfg<3, 2, 8>(),   // 24 x 128
-        make_cfg<2, 2, 8>(),   // 16 x 128 (small images)
-        make_cfg<3, 2, 12>(),  // 36 x 128, 12 px/thread, 3 warps per sub-partition (<= 168 registers)
+        make_cfg<5, 4, 8>(),   // 40 rows x 128 cols, 20 px/thread
+        make_cfg<4, 4, 8>(),   // 32 x 128
+        make_cfg<3, 4, 8>(),   // 24 x 128
+        make_cfg<2, 4, 8>(),   // 16 x 128 (small images)
     };
     return v;
 }
@@ -783,9 +717,9 @@ int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len
     long useful = 0;
     for (int i = 0; i < plan.n_strips; ++i) useful += plan.ux1[i] - plan.ux0[i];
     return snprintf(buf, len,
-                    "cluster: patch %d rows x 2x%d cols/thread (FFMA2 pairs), %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
+                    "cluster: patch %dx%d px/thread, %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
                     "%d strip(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
-                    k.PR, k.PCH, k.NW, k.RB(), k.TW(), plan.cs, plan.cs * k.RB(), plan.n_strips, (long)B * C * plan.n_strips,
+                    k.PR, k.PC, k.NW, k.RB(), k.TW(), plan.cs, plan.cs * k.RB(), plan.n_strips, (long)B * C * plan.n_strips,
                     plan.max_clusters, (double)useful * H / ((double)plan.n_strips * k.TW() * plan.cs * k.RB()), k.smem);
 }
 
