@@ -144,7 +144,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
 //   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
 //   then cbuf[RB][TW]         folded constant term c' of the current task
-//   then 3 mbarriers          tma, full[0], full[1]
+//   then mbarriers            tma, slot_full[2][2*NW+2]  (one per exchanged row and parity: a warp synchronises only
+//                             with the producers of the two rows it reads, never with the whole CTA)
 //
 // Arithmetic is scalar FFMA on purpose.  fma.rn.f32x2 (FFMA2, new on sm_100) was tried with pixel pairs in 64-bit
 // registers: with 160 weight registers live per thread it sustains only ~0.22 FFMA2/clk per sub-partition (715 cycles
@@ -165,7 +166,9 @@ struct Cfg {
     // the folded constant term c' (one float per pixel) lives in shared memory: it is read once per pixel and
     // iteration (one LDS.128 per patch row), which frees PR*PC registers per thread
     static constexpr size_t kCBytes = (size_t)RB * TW * sizeof(float);
-    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 64;
+    // mbarriers: [0] TMA stage; then one per (parity, slot) of the row exchange
+    static constexpr int kNumBars = 1 + 2 * kSlots;
+    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 8 * kNumBars;
     static_assert(PC == 4, "vectorised global/shared accesses below assume 4 columns per thread");
     static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
@@ -183,6 +186,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // the neighbour is 0: either the image border (zero padding) or strip halo that decays.
 template <int PC>
 __device__ __forceinline__ void row_edges(const float (&v)[PC], float (&ed)[2], bool first_lane, bool last_lane) {
+#ifdef CSPN_ABLATE_NO_SHFL   // timing experiment only: wrong results
+    ed[0] = v[PC - 1]; ed[1] = v[0]; return;
+#endif
     const float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
     const float r = __shfl_down_sync(0xffffffffu, v[0], 1);
     ed[0] = first_lane ? 0.f : l;
@@ -239,34 +245,38 @@ __device__ __forceinline__ void store_row_remote_if(uint32_t addr, const float (
 // Per-thread constants of the row exchange.
 struct Xch {
     float* base;          // xch + lane*PC (parity 0, slot 0)
-    uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
-    uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
+    uint32_t bar_slot0;   // mbarrier of (parity 0, slot 0); slot s of parity p is 8*(p*kSlots + s) bytes further
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
-    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
-    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
-    bool has_up, has_dn;
-    // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
-    // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
-    bool remote_up, remote_dn, sig_tx, sig;
+    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, and that slot's barrier
+    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above") and its barrier
+    // roles as predicates (branch-free publish): remote_* = this warp owns the CTA's top / bottom row and the
+    // neighbour CTA exists; sig = lane 0 (signals the barriers of the two rows this warp produces);
+    // arm_up / arm_dn = lane 0 of the warp that CONSUMES a remote halo row arms that slot's tx count
+    bool remote_up, remote_dn, sig, arm_up, arm_dn;
+    bool wait_up, wait_dn;      // false only where the row above / below the patch lies outside the image for good
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
-// halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
+// halo slots through DSMEM) and signal the barrier of each row.  Branch-free: roles are predicates.
 template <int PR, int PC, int NW, int PAR>
 __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
     using K = Cfg<PR, PC, NW>;
     float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
     store_row_smem(p + (1 + 2 * wy) * K::TW, top);
     store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
-    const uint32_t bar = x.bar_full0 + 8 * PAR;
-    // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
-    store_row_remote_if(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR, x.remote_up);
-    store_row_remote_if(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR, x.remote_dn);
+    // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below;
+    // the st.async completes (complete_tx) on the consumer's barrier of that slot
+    store_row_remote_if(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR * K::kSlots, x.remote_up);
+    store_row_remote_if(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR * K::kSlots, x.remote_dn);
     __syncwarp();
-    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
-    mbar_arrive_if(bar, x.sig);
+    const uint32_t bar = x.bar_slot0 + 8 * (PAR * K::kSlots + 1 + 2 * wy);
+    mbar_arrive_if(bar, x.sig);          // top row ready
+    mbar_arrive_if(bar + 8, x.sig);      // bottom row ready
+    // the consumer of a remote halo row arms the bytes it expects for the same step
+    mbar_arrive_expect_tx_if(x.bar_slot0 + 8 * (PAR * K::kSlots), K::TW * 4, x.arm_up);
+    mbar_arrive_expect_tx_if(x.bar_slot0 + 8 * (PAR * K::kSlots + K::kSlots - 1), K::TW * 4, x.arm_dn);
 }
 
 // One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
@@ -292,7 +302,10 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
         if (rs + 1 < PR) scatter_row<PC, -1>(w[rs + 1], src, dout[rs + 1]);  // source is the row above row rs+1
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
-    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+#ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
+    if (x.wait_up) mbar_wait(x.bar_slot0 + 8 * (PAR * K::kSlots + 2 * wy), phase);        // row above is published
+    if (x.wait_dn) mbar_wait(x.bar_slot0 + 8 * (PAR * K::kSlots + 2 * wy + 3), phase);    // row below is published
+#endif
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
         float u[PC], ue[2], d[PC], de[2];
@@ -304,7 +317,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
         scatter_row<PC, +1>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1]);
     }
     if constexpr (PUBLISH) {
+#ifndef CSPN_ABLATE_NO_SYNC
         publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+#endif
         // ---- tail: x-edges of the new rows, for the next step ------------------------------------------------
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
@@ -321,7 +336,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
     float* cbuf = reinterpret_cast<float*>(smem_raw + K::kStageBytes + K::kXchBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes + K::kCBytes);
-    const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
+    const uint32_t bar_tma = smem_u32(bars), bar_slot0 = smem_u32(bars + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
@@ -330,20 +345,21 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const int y_thr = band_y0 + wy * PR;    // first row of this thread
     const size_t HW = (size_t)H * W;
 
+    const bool has_up = crank > 0, has_dn = crank + 1 < csize;
     Xch xc;
     xc.base = xch + lane * PC;
-    xc.bar_full0 = bar_full0;
-    xc.has_up = crank > 0;
-    xc.has_dn = crank + 1 < csize;
-    xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
-    xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
-    xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
-    xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
-    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
-    xc.remote_up = xc.has_up && wy == 0;
-    xc.remote_dn = xc.has_dn && wy == NW - 1;
-    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
-    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
+    xc.bar_slot0 = bar_slot0;
+    xc.up_data = has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
+    xc.up_bar = has_up ? map_to_cta(bar_slot0 + 8 * (K::kSlots - 1), crank - 1) : 0u;
+    xc.dn_data = has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
+    xc.dn_bar = has_dn ? map_to_cta(bar_slot0, crank + 1) : 0u;
+    xc.remote_up = has_up && wy == 0;
+    xc.remote_dn = has_dn && wy == NW - 1;
+    xc.sig = lane == 0;
+    xc.arm_up = lane == 0 && wy == 0 && has_up;
+    xc.arm_dn = lane == 0 && wy == NW - 1 && has_dn;
+    xc.wait_up = wy > 0 || has_up;        // the band's first row has no producer when the CTA is the first of the cluster
+    xc.wait_dn = wy < NW - 1 || has_dn;
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
@@ -367,8 +383,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        mbar_init(bar_full0, NW);
-        mbar_init(bar_full0 + 8, NW);
+        for (int i = 0; i < 2 * K::kSlots; ++i) mbar_init(bar_slot0 + 8 * i, 1);   // one producer (or one arming consumer) each
         fence_barrier_init();
         fence_proxy_async();
         if (task < n_tasks) issue_stage(task);
@@ -376,16 +391,18 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     // every CTA's barriers must be initialised before a neighbour's st.async can target them
     cluster_arrive();
     // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
-    if (!xc.has_up)
+    if (!has_up)
         for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
-    if (!xc.has_dn)
+    if (!has_dn)
         for (int i = tid; i < TW; i += K::kThreads) {
             xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
             xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
         }
     cluster_wait();
 
-    uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
+    // phase parities: the TMA barrier, and the exchange barriers of parity 0 / 1 (each completes once per two steps;
+    // they run on across tasks)
+    uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
         const int strip = task % prm.n_strips;
@@ -501,7 +518,9 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
         first = false;
         const int iters = prm.iters;
+#ifndef CSPN_ABLATE_NO_SYNC
         publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+#endif
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
