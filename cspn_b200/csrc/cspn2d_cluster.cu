@@ -46,6 +46,7 @@ struct ClusterParams {
     float* out;           // [B*C][H][W]
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_tasks;
+    int zero;                 // always 0 (run-time constant the compiler cannot fold)
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -144,8 +145,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
 //   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
 //   then cbuf[RB][TW]         folded constant term c' of the current task
-//   then mbarriers            tma, slot_full[2][2*NW+2]  (one per exchanged row and parity: a warp synchronises only
-//                             with the producers of the two rows it reads, never with the whole CTA)
+//   then 3 mbarriers          tma, full[0], full[1]
 //
 // Arithmetic is scalar FFMA on purpose.  fma.rn.f32x2 (FFMA2, new on sm_100) was tried with pixel pairs in 64-bit
 // registers: with 160 weight registers live per thread it sustains only ~0.22 FFMA2/clk per sub-partition (715 cycles
@@ -166,9 +166,7 @@ struct Cfg {
     // the folded constant term c' (one float per pixel) lives in shared memory: it is read once per pixel and
     // iteration (one LDS.128 per patch row), which frees PR*PC registers per thread
     static constexpr size_t kCBytes = (size_t)RB * TW * sizeof(float);
-    // mbarriers: [0] TMA stage; then one per (parity, slot) of the row exchange
-    static constexpr int kNumBars = 1 + 2 * kSlots;
-    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 8 * kNumBars;
+    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 64;
     static_assert(PC == 4, "vectorised global/shared accesses below assume 4 columns per thread");
     static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
@@ -234,53 +232,50 @@ __device__ __forceinline__ void load_row_smem(const float* p, float (&v)[4]) {
 __device__ __forceinline__ void store_row_smem(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
-__device__ __forceinline__ void store_row_remote_if(uint32_t addr, const float (&v)[4], uint32_t bar, bool pred) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
-        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n}\n" ::"r"(addr),
-        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar), "r"((int)pred)
-        : "memory");
+__device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)[4], uint32_t bar) {
+    st_async_v4(addr, make_float4(v[0], v[1], v[2], v[3]), bar);
 }
 
 // Per-thread constants of the row exchange.
 struct Xch {
     float* base;          // xch + lane*PC (parity 0, slot 0)
-    uint32_t bar_slot0;   // mbarrier of (parity 0, slot 0); slot s of parity p is 8*(p*kSlots + s) bytes further
+    uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
+    uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
-    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, and that slot's barrier
-    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above") and its barrier
-    // roles as predicates (branch-free publish): remote_* = this warp owns the CTA's top / bottom row and the
-    // neighbour CTA exists; sig = lane 0 (signals the barriers of the two rows this warp produces);
-    // arm_up / arm_dn = lane 0 of the warp that CONSUMES a remote halo row arms that slot's tx count
-    bool remote_up, remote_dn, sig, arm_up, arm_dn;
-    bool wait_up, wait_dn;      // false only where the row above / below the patch lies outside the image for good
+    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
+    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
+    bool has_up, has_dn;
+    // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
+    // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
+    bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
+    uint32_t zero;        // 0, but only known at run time (see iterate)
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
-// halo slots through DSMEM) and signal the barrier of each row.  Branch-free: roles are predicates.
+// halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
 template <int PR, int PC, int NW, int PAR>
 __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
     using K = Cfg<PR, PC, NW>;
     float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
     store_row_smem(p + (1 + 2 * wy) * K::TW, top);
     store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
-    // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below;
-    // the st.async completes (complete_tx) on the consumer's barrier of that slot
-    store_row_remote_if(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR * K::kSlots, x.remote_up);
-    store_row_remote_if(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR * K::kSlots, x.remote_dn);
+    const uint32_t bar = x.bar_full0 + 8 * PAR;
+    // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
+    // (remote_up / remote_dn are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform
+    // branches, not divergence regions)
+    if (x.remote_up) store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
+    if (x.remote_dn) store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
     __syncwarp();
-    const uint32_t bar = x.bar_slot0 + 8 * (PAR * K::kSlots + 1 + 2 * wy);
-    mbar_arrive_if(bar, x.sig);          // top row ready
-    mbar_arrive_if(bar + 8, x.sig);      // bottom row ready
-    // the consumer of a remote halo row arms the bytes it expects for the same step
-    mbar_arrive_expect_tx_if(x.bar_slot0 + 8 * (PAR * K::kSlots), K::TW * 4, x.arm_up);
-    mbar_arrive_expect_tx_if(x.bar_slot0 + 8 * (PAR * K::kSlots + K::kSlots - 1), K::TW * 4, x.arm_dn);
+    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
+    mbar_arrive_if(bar, x.sig);
 }
 
 // One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
 // into PAR^1 (not on the last step).  Two register sets alternate as input and output: nothing is copied.
+// On entry dout already holds c' (the accumulators' seed); on exit din -- dead by then, and the output set of the next
+// step -- is re-seeded with c' from shared memory, so that load has a whole exchange to land.
 //
 // Ordering is what makes the exchange free: every source row the thread owns is scattered into the accumulators
 // BEFORE the mbarrier wait; after the wait only the rows above / below the patch remain (3 taps of the two boundary
@@ -288,12 +283,10 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
 // the tail, off the critical path of the other warps.
 template <int PR, int PC, int NW, int PAR, bool PUBLISH>
 __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
-                                        const float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
+                                        float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
                                         float (&eout)[PR][2]) {
     using K = Cfg<PR, PC, NW>;
-    // ---- before the wait: accumulators start from c', then every own source row is scattered ----------------
-#pragma unroll
-    for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
+    // ---- before the wait: every own source row is scattered into the (pre-seeded) accumulators ---------------
 #pragma unroll
     for (int rs = 0; rs < PR; ++rs) {
         const Row<PC> src{din[rs], ein[rs]};
@@ -303,8 +296,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
 #ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
-    if (x.wait_up) mbar_wait(x.bar_slot0 + 8 * (PAR * K::kSlots + 2 * wy), phase);        // row above is published
-    if (x.wait_dn) mbar_wait(x.bar_slot0 + 8 * (PAR * K::kSlots + 2 * wy + 3), phase);    // row below is published
+    // The barrier address is made to depend on an accumulator of the scatter phase (x.zero is 0 at run time, unknown
+    // at compile time): ptxas would otherwise hoist the try_wait -- and the spin on it -- above that phase.
+    mbar_wait(x.bar_full0 + 8 * PAR + (__float_as_uint(dout[PR / 2][PC - 1]) & x.zero), phase);
 #endif
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
@@ -320,7 +314,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
 #ifndef CSPN_ABLATE_NO_SYNC
         publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
 #endif
-        // ---- tail: x-edges of the new rows, for the next step ------------------------------------------------
+        // ---- tail: seed the next step's accumulators, x-edges of the new rows ---------------------------------
+#pragma unroll
+        for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
     }
@@ -336,33 +332,34 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
     float* cbuf = reinterpret_cast<float*>(smem_raw + K::kStageBytes + K::kXchBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes + K::kCBytes);
-    const uint32_t bar_tma = smem_u32(bars), bar_slot0 = smem_u32(bars + 1);
+    const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wy = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform for the compiler
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const int H = prm.H, W = prm.W;
     const int band_y0 = (int)crank * RB;
     const int y_thr = band_y0 + wy * PR;    // first row of this thread
     const size_t HW = (size_t)H * W;
 
-    const bool has_up = crank > 0, has_dn = crank + 1 < csize;
     Xch xc;
     xc.base = xch + lane * PC;
-    xc.bar_slot0 = bar_slot0;
-    xc.up_data = has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
-    xc.up_bar = has_up ? map_to_cta(bar_slot0 + 8 * (K::kSlots - 1), crank - 1) : 0u;
-    xc.dn_data = has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
-    xc.dn_bar = has_dn ? map_to_cta(bar_slot0, crank + 1) : 0u;
-    xc.remote_up = has_up && wy == 0;
-    xc.remote_dn = has_dn && wy == NW - 1;
-    xc.sig = lane == 0;
-    xc.arm_up = lane == 0 && wy == 0 && has_up;
-    xc.arm_dn = lane == 0 && wy == NW - 1 && has_dn;
-    xc.wait_up = wy > 0 || has_up;        // the band's first row has no producer when the CTA is the first of the cluster
-    xc.wait_dn = wy < NW - 1 || has_dn;
+    xc.bar_full0 = bar_full0;
+    xc.has_up = crank > 0;
+    xc.has_dn = crank + 1 < csize;
+    xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
+    xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
+    xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
+    xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
+    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
+    xc.remote_up = xc.has_up && wy == 0;
+    xc.remote_dn = xc.has_dn && wy == NW - 1;
+    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
+    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
+    xc.zero = (uint32_t)prm.zero;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -383,7 +380,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        for (int i = 0; i < 2 * K::kSlots; ++i) mbar_init(bar_slot0 + 8 * i, 1);   // one producer (or one arming consumer) each
+        mbar_init(bar_full0, NW);
+        mbar_init(bar_full0 + 8, NW);
         fence_barrier_init();
         fence_proxy_async();
         if (task < n_tasks) issue_stage(task);
@@ -391,18 +389,16 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     // every CTA's barriers must be initialised before a neighbour's st.async can target them
     cluster_arrive();
     // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
-    if (!has_up)
+    if (!xc.has_up)
         for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
-    if (!has_dn)
+    if (!xc.has_dn)
         for (int i = tid; i < TW; i += K::kThreads) {
             xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
             xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
         }
     cluster_wait();
 
-    // phase parities: the TMA barrier, and the exchange barriers of parity 0 / 1 (each completes once per two steps;
-    // they run on across tasks)
-    uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;
+    uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
         const int strip = task % prm.n_strips;
@@ -525,6 +521,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
         float d2[PR][PC], e2[PR][2];    // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
+#pragma unroll
+        for (int r = 0; r < PR; ++r) load_row_smem(xc.cbuf + r * TW, d2[r]);   // accumulators of the first step start from c'
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
             iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
@@ -777,6 +775,7 @@ int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
     prm.blur = p.blur; prm.sparse = p.sparse; prm.out = p.out;
     prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = p.iters; prm.norm_abs = p.norm_abs;
     prm.n_strips = plan.n_strips;
+    prm.zero = 0;
     prm.n_tasks = (int)((long)p.B * p.C * plan.n_strips);
     for (int i = 0; i < kMaxStrips; ++i) {
         prm.tile_x0[i] = i < plan.n_strips ? plan.tile_x0[i] : 0;
