@@ -235,6 +235,13 @@ __device__ __forceinline__ void store_row_smem(float* p, const float (&v)[4]) {
 __device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)[4], uint32_t bar) {
     st_async_v4(addr, make_float4(v[0], v[1], v[2], v[3]), bar);
 }
+__device__ __forceinline__ void store_row_remote_if(uint32_t addr, const float (&v)[4], uint32_t bar, bool pred) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
+        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n}\n" ::"r"(addr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar), "r"((int)pred)
+        : "memory");
+}
 
 // Per-thread constants of the row exchange.
 struct Xch {
@@ -265,8 +272,13 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
     // (remote_up / remote_dn are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform
     // branches, not divergence regions)
+#ifdef CSPN_VAR_PRED_STAS
+    store_row_remote_if(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR, x.remote_up);
+    store_row_remote_if(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR, x.remote_dn);
+#else
     if (x.remote_up) store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
     if (x.remote_dn) store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
+#endif
     __syncwarp();
     mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
     mbar_arrive_if(bar, x.sig);
@@ -286,6 +298,10 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
                                         float (&eout)[PR][2]) {
     using K = Cfg<PR, PC, NW>;
+#ifdef CSPN_VAR_SEED_AT_START
+#pragma unroll
+    for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
+#endif
     // ---- before the wait: every own source row is scattered into the (pre-seeded) accumulators ---------------
 #pragma unroll
     for (int rs = 0; rs < PR; ++rs) {
@@ -298,7 +314,11 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
 #ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
     // The barrier address is made to depend on an accumulator of the scatter phase (x.zero is 0 at run time, unknown
     // at compile time): ptxas would otherwise hoist the try_wait -- and the spin on it -- above that phase.
+#ifdef CSPN_VAR_EARLY_WAIT
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+#else
     mbar_wait(x.bar_full0 + 8 * PAR + (__float_as_uint(dout[PR / 2][PC - 1]) & x.zero), phase);
+#endif
 #endif
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
@@ -315,8 +335,10 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
         publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
 #endif
         // ---- tail: seed the next step's accumulators, x-edges of the new rows ---------------------------------
+#ifndef CSPN_VAR_SEED_AT_START
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
+#endif
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
     }
@@ -335,7 +357,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
 
     const int tid = threadIdx.x, lane = tid & 31;
+#ifdef CSPN_VAR_PLAIN_WY
+    const int wy = tid >> 5;
+#else
     const int wy = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform for the compiler
+#endif
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const int H = prm.H, W = prm.W;
     const int band_y0 = (int)crank * RB;
@@ -604,6 +630,16 @@ struct OccKey { int cfg, cs, dev; };
 std::vector<std::pair<OccKey, int>> g_occ_cache;
 bool g_attr_set[16][16] = {};
 
+int sm_count(int dev) {
+    static int cached[16] = {};
+    if (!cached[dev & 15]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        cached[dev & 15] = n;
+    }
+    return cached[dev & 15];
+}
+
 // how many clusters of `cs` CTAs of configuration `ci` can be co-resident on the device
 int max_active_clusters(int ci, int cs, int dev) {
     for (auto& e : g_occ_cache)
@@ -677,7 +713,10 @@ bool make_plan(int B, int C, int H, int W, int iters, int dev, Plan& best, char*
         if (mac <= 0) continue;
         // Steady-state cost per image: strips x per-task work / co-resident clusters.  Deliberately independent of
         // B and C, so the same image gets the same tiling (hence bit-identical results) whatever batch it is part of.
-        p.cost = (double)p.n_strips * k.RB() * k.TW() * (8.0 * iters + 60.0) / mac;
+        // (when a small configuration fits two CTAs per SM, those CTAs share the SM's FMA pipe: count SMs, not CTAs)
+        const int n_sms = dev >= 0 ? sm_count(dev) : 148;
+        const int ctas_per_sm = (mac * cs + n_sms - 1) / n_sms;
+        p.cost = (double)p.n_strips * k.RB() * k.TW() * (8.0 * iters + 60.0) * ctas_per_sm / mac;
         p.cfg = ci; p.cs = cs; p.max_clusters = mac;
         if (best.cfg < 0 || p.cost < best.cost) best = p;
     }

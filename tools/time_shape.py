@@ -4,6 +4,12 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+try:
+    import pynvml
+    pynvml.nvmlInit(); _h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    def clk(): return pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM)
+except Exception:
+    def clk(): return -1
 
 import cspn_b200
 from cspn_b200.synth import make_inputs
@@ -23,7 +29,8 @@ for i in range(0, len(args), 4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); cspn_b200.propagate2d(g, d, s, N, '8sum', algo); b.record(); evs.append((a, b))
     torch.cuda.synchronize()
+    c_mhz = clk()
     ms = sorted(a.elapsed_time(b) for a, b in evs)
     px = B * H * W
     print(f'B={B} H={H} W={W} N={N}: median {ms[5]*1e3:.1f} us  min {ms[0]*1e3:.1f} us  {px/ms[5]/1e3:.0f} Mpx/s  '
-          f'{44*px/ms[5]/1e6:.0f} GB/s algorithmic | {cspn_b200.describe_plan(B, 1, H, W, N, algo)}', flush=True)
+          f'{44*px/ms[5]/1e6:.0f} GB/s algorithmic  sm_clk={c_mhz} MHz | {cspn_b200.describe_plan(B, 1, H, W, N, algo)}', flush=True)
