@@ -46,7 +46,6 @@ struct ClusterParams {
     float* out;           // [B*C][H][W]
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_tasks;
-    int zero;                 // always 0 (run-time constant the compiler cannot fold)
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -235,13 +234,6 @@ __device__ __forceinline__ void store_row_smem(float* p, const float (&v)[4]) {
 __device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)[4], uint32_t bar) {
     st_async_v4(addr, make_float4(v[0], v[1], v[2], v[3]), bar);
 }
-__device__ __forceinline__ void store_row_remote_if(uint32_t addr, const float (&v)[4], uint32_t bar, bool pred) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
-        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n}\n" ::"r"(addr),
-        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(bar), "r"((int)pred)
-        : "memory");
-}
 
 // Per-thread constants of the row exchange.
 struct Xch {
@@ -256,7 +248,6 @@ struct Xch {
     // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
     bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
-    uint32_t zero;        // 0, but only known at run time (see iterate)
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
@@ -272,13 +263,8 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
     // (remote_up / remote_dn are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform
     // branches, not divergence regions)
-#ifdef CSPN_VAR_PRED_STAS
-    store_row_remote_if(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR, x.remote_up);
-    store_row_remote_if(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR, x.remote_dn);
-#else
     if (x.remote_up) store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
     if (x.remote_dn) store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
-#endif
     __syncwarp();
     mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
     mbar_arrive_if(bar, x.sig);
@@ -298,10 +284,6 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
                                         float (&eout)[PR][2]) {
     using K = Cfg<PR, PC, NW>;
-#ifdef CSPN_VAR_SEED_AT_START
-#pragma unroll
-    for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
-#endif
     // ---- before the wait: every own source row is scattered into the (pre-seeded) accumulators ---------------
 #pragma unroll
     for (int rs = 0; rs < PR; ++rs) {
@@ -312,13 +294,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
 #ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
-    // The barrier address is made to depend on an accumulator of the scatter phase (x.zero is 0 at run time, unknown
-    // at compile time): ptxas would otherwise hoist the try_wait -- and the spin on it -- above that phase.
-#ifdef CSPN_VAR_EARLY_WAIT
+    // (ptxas issues the try_wait early and only branches on its result here, after part of the scatter phase; forcing
+    // it later through a data dependency measured slower: 427 vs 408 us on the 32x1216x352 workload.)
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
-#else
-    mbar_wait(x.bar_full0 + 8 * PAR + (__float_as_uint(dout[PR / 2][PC - 1]) & x.zero), phase);
-#endif
 #endif
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
@@ -335,10 +313,8 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
         publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
 #endif
         // ---- tail: seed the next step's accumulators, x-edges of the new rows ---------------------------------
-#ifndef CSPN_VAR_SEED_AT_START
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
-#endif
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
     }
@@ -357,11 +333,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
 
     const int tid = threadIdx.x, lane = tid & 31;
-#ifdef CSPN_VAR_PLAIN_WY
-    const int wy = tid >> 5;
-#else
     const int wy = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform for the compiler
-#endif
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const int H = prm.H, W = prm.W;
     const int band_y0 = (int)crank * RB;
@@ -385,7 +357,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
-    xc.zero = (uint32_t)prm.zero;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -814,7 +785,6 @@ int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
     prm.blur = p.blur; prm.sparse = p.sparse; prm.out = p.out;
     prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = p.iters; prm.norm_abs = p.norm_abs;
     prm.n_strips = plan.n_strips;
-    prm.zero = 0;
     prm.n_tasks = (int)((long)p.B * p.C * plan.n_strips);
     for (int i = 0; i < kMaxStrips; ++i) {
         prm.tile_x0[i] = i < plan.n_strips ? plan.tile_x0[i] : 0;
