@@ -62,6 +62,11 @@ bool cluster2d_supported(const Problem2D& p, char* why, int why_len);
 int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches);
 int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len);
 
+void launch_prep2d(const float* guidance, const float* sparse, float* wk, int B, int H, int W, int gch, int norm_abs,
+                   cudaStream_t stream);
+void launch_step2d(const float* wk, const float* d0, const float* cur, float* dst, int B, int C, int H, int W,
+                   cudaStream_t stream);
+
 size_t bwd2d_workspace_bytes(int B, int C, int H, int W, int iters);
 int bwd2d(const Problem2D& p, const float* grad_out, float* grad_guidance, float* grad_blur, void* ws,
           size_t ws_bytes, cudaStream_t stream, int* launches);

@@ -75,6 +75,18 @@ step2d_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const 
 
 }  // namespace
 
+// launchers shared with the backward pass (cspn2d_bwd.cu)
+void launch_prep2d(const float* guidance, const float* sparse, float* wk, int B, int H, int W, int gch, int norm_abs,
+                   cudaStream_t stream) {
+    const dim3 block(32, 8);
+    prep2d_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B), block, 0, stream>>>(guidance, sparse, wk, H, W, gch, norm_abs);
+}
+void launch_step2d(const float* wk, const float* d0, const float* cur, float* dst, int B, int C, int H, int W,
+                   cudaStream_t stream) {
+    const dim3 block(32, 8);
+    step2d_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B * C), block, 0, stream>>>(wk, d0, cur, dst, C, H, W);
+}
+
 size_t generic2d_workspace_bytes(int B, int C, int H, int W, int iters) {
     if (iters <= 0) return 0;
     const size_t HW = (size_t)H * W;
