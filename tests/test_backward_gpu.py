@@ -54,5 +54,5 @@ def test_training_step_through_the_module():
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(loss.item())
     assert not torch.equal(net.weight, w0) and all(l == l for l in losses)
