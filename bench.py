@@ -144,16 +144,17 @@ def cpu_baseline_leg():
     mpx, per = time_torch_port(nb, 2, 1, threads)
     g, d, s = make_inputs(0, 8, 1, H, W)
     gn, dn, sn = g.numpy(), d.numpy(), s.numpy()
-    c_oracle.cspn2d(gn[:1], dn[:1], sn[:1], ITERS, NORM)
+    ncpu = os.cpu_count() or 1
+    c_oracle.cspn2d(gn[:1], dn[:1], sn[:1], ITERS, NORM, nthreads=ncpu)
     t0 = time.perf_counter()
-    c_oracle.cspn2d(gn, dn, sn, ITERS, NORM)
+    c_oracle.cspn2d(gn, dn, sn, ITERS, NORM, nthreads=ncpu)
     c_mpx = 8 * H * W / (time.perf_counter() - t0) / 1e6
     return {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'cores': threads, 'kind': 'port',
             'sample': f'{nb}x{W}x{H} images, {ITERS} iters, 1 warm-up + 2 timed forwards of oracle/cspn_torch_port.py '
                       f'(the reference op sequence of cspn.py:42-83 on CPU; /root/reference is absent on this box); '
                       f'{threads} torch threads = the fastest of 4..{os.cpu_count()} on this host',
             'host_cpus': os.cpu_count(),
-            'c_openmp_port_mpx_s': round(c_mpx, 3), 'c_openmp_threads': c_oracle.max_threads()}
+            'c_openmp_port_mpx_s': round(c_mpx, 3), 'c_openmp_threads': ncpu}
 
 
 def run_reference_arm(args):
@@ -161,9 +162,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads, t1 = best_torch_threads()
+    threads, _ = best_torch_threads()
     budget = 150.0                                               # seconds for the whole run
-    nb = max(1, min(B_PER_GPU, int(budget / ((args.steps + args.warmup) * max(t1, 1e-3)))))
+    t_img = time_torch_port(4, 1, 1, threads)[1] / 4             # per-image time at a batch that no longer fits the caches
+    nb = max(1, min(B_PER_GPU, int(budget / ((args.steps + args.warmup) * max(t_img, 1e-3)))))
     mpx, per = time_torch_port(nb, args.steps, args.warmup, threads)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': round(mpx, 3), 'unit': 'Mpixels/s', 'n_gpus': args.gpus,
@@ -299,7 +301,7 @@ def main():
     gather = None
     if world > 1:
         full = torch.empty(world * B_PER_GPU, 1, H, W, device=dev)
-        for _ in range(2):
+        for _ in range(5):
             dist.all_gather_into_tensor(full, out)
         barrier()
         ev0.record()
