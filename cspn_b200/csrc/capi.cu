@@ -1,5 +1,6 @@
 // extern "C" surface of libcspn_b200.so (include/cspn_b200.h): argument checking, algorithm
 // dispatch, and the chunked host-buffer pipeline behind the *_host entry points.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -224,7 +225,10 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
     const size_t HW = (size_t)H * W;
     // chunk: about 48 MB of input per slot keeps PCIe transfers long and the kernel grid full
     const size_t per_img = (8 + C + (sparse ? 1 : 0)) * HW * sizeof(float);
-    int nb = (int)((48u << 20) / per_img);
+    // developer hook for tuning runs: CSPN_B200_HOST_CHUNK_MB overrides the chunk size
+    const char* chunk_env = getenv("CSPN_B200_HOST_CHUNK_MB");
+    const size_t chunk_bytes = (size_t)(chunk_env && atoi(chunk_env) > 0 ? atoi(chunk_env) : 48) << 20;
+    int nb = (int)(chunk_bytes / per_img);
     if (nb < 1) nb = 1;
     if (nb > B) nb = B;
     // keep at least 3 chunks in flight when the batch allows it
