@@ -53,14 +53,15 @@ def propagate2d(guidance, blur_depth, sparse_depth=None, prop_time=24, norm_type
     g = guidance.contiguous()
     d = blur_depth.contiguous()
     s = None if sparse_depth is None else sparse_depth.contiguous()
-    out = torch.empty_like(d)
     if not d.is_cuda:
         if not torch.cuda.is_available():
             raise _lib.CspnError('cspn_b200 needs a CUDA device (no CPU implementation exists in this package)')
+        out = torch.empty_like(d, pin_memory=d.is_pinned())     # pinned in -> pinned out: the D2H stays asynchronous
         rc = L.cspn2d_fwd_f32_host(_ptr(g), _ptr(d), _ptr(s), _ptr(out), B, C, H, W, g.shape[1], int(prop_time),
                                    NORM2D[norm_type], algo, torch.cuda.current_device())
         _lib.check(rc, 'cspn2d_fwd_f32_host')
         return out
+    out = torch.empty_like(d)
     with torch.cuda.device(d.device):
         ws_bytes = L.cspn2d_workspace_bytes(B, C, H, W, int(prop_time), algo)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d.device) if ws_bytes else None
@@ -143,14 +144,15 @@ def propagate3d(guidance, feat, prop_time=12, norm_type='26sum_abs'):
         return feat
     L = _lib.lib()
     g, f = guidance.contiguous(), feat.contiguous()
-    out = torch.empty_like(f)
     if not f.is_cuda:
         if not torch.cuda.is_available():
             raise _lib.CspnError('cspn_b200 needs a CUDA device (no CPU implementation exists in this package)')
+        out = torch.empty_like(f, pin_memory=f.is_pinned())
         rc = L.cspn3d_fwd_f32_host(_ptr(g), _ptr(f), _ptr(out), B, C, D, H, W, int(prop_time), NORM3D[norm_type],
                                    torch.cuda.current_device())
         _lib.check(rc, 'cspn3d_fwd_f32_host')
         return out
+    out = torch.empty_like(f)
     with torch.cuda.device(f.device):
         ws_bytes = L.cspn3d_workspace_bytes(B, C, D, H, W, int(prop_time))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device) if ws_bytes else None

@@ -250,10 +250,15 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
         float* dout = reinterpret_cast<float*>(s.buf + g_bytes + d_bytes);
         float* dsp = sparse ? reinterpret_cast<float*>(s.buf + g_bytes + 2 * d_bytes) : nullptr;
         void* dws = ws_bytes ? s.buf + g_bytes + 2 * d_bytes + s_bytes : nullptr;
-        // only channels 0..7 of the guidance are used (cspn.py:91-98): copy just those planes
-        CSPN_CUDA_TRY(cudaMemcpy2DAsync(dg, 8 * HW * sizeof(float), guidance + (size_t)b0 * guidance_channels * HW,
-                                        (size_t)guidance_channels * HW * sizeof(float), 8 * HW * sizeof(float), n,
-                                        cudaMemcpyHostToDevice, s.stream));
+        // only channels 0..7 of the guidance are used (cspn.py:91-98): copy just those planes.  (A pitched 2D copy
+        // runs at ~20 GB/s on this platform against 48 GB/s for a linear one, so it is used only when needed.)
+        if (guidance_channels == 8)
+            CSPN_CUDA_TRY(cudaMemcpyAsync(dg, guidance + (size_t)b0 * 8 * HW, (size_t)n * 8 * HW * sizeof(float),
+                                          cudaMemcpyHostToDevice, s.stream));
+        else
+            for (int i = 0; i < n; ++i)
+                CSPN_CUDA_TRY(cudaMemcpyAsync(dg + (size_t)i * 8 * HW, guidance + (size_t)(b0 + i) * guidance_channels * HW,
+                                              8 * HW * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         CSPN_CUDA_TRY(cudaMemcpyAsync(dd, blur + (size_t)b0 * C * HW, (size_t)n * C * HW * sizeof(float),
                                       cudaMemcpyHostToDevice, s.stream));
         if (sparse)
