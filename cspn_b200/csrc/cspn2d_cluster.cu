@@ -46,7 +46,6 @@ struct ClusterParams {
     float* out;           // [B*C][H][W]
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_tasks;
-    int zero;                 // always 0 (a run-time constant the compiler cannot fold)
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -84,20 +83,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
-}
-// one non-blocking probe: 1 if the phase with this parity has completed
-__device__ __forceinline__ uint32_t mbar_try_once(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done;
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -263,7 +248,6 @@ struct Xch {
     // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
     bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
-    uint32_t zero;        // 0, but only known at run time (see iterate)
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
@@ -300,10 +284,6 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
                                         float (&eout)[PR][2]) {
     using K = Cfg<PR, PC, NW>;
-    // Probe the exchange barrier now (the probe's ~100-cycle round trip hides behind the scatter phase) ...
-#ifndef CSPN_ABLATE_NO_SYNC
-    const uint32_t ready = mbar_try_once(x.bar_full0 + 8 * PAR, phase);
-#endif
     // ---- before the wait: every own source row is scattered into the (pre-seeded) accumulators ---------------
 #pragma unroll
     for (int rs = 0; rs < PR; ++rs) {
@@ -314,9 +294,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
 #ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
-    // ... and only block if that probe failed.  The branch is tied to a late accumulator (x.zero is 0 at run time,
-    // unknown at compile time) so that ptxas cannot resolve it -- and stall a fast warp -- before the scatter phase.
-    if (!(ready | (__float_as_uint(dout[PR / 2][PC - 1]) & x.zero))) mbar_wait(x.bar_full0 + 8 * PAR, phase);
+    // (ptxas issues the try_wait early and only branches on its result here, after part of the scatter phase; forcing
+    // it later through a data dependency measured slower: 427 vs 408 us on the 32x1216x352 workload.)
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
 #endif
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
@@ -377,7 +357,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
-    xc.zero = (uint32_t)prm.zero;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -806,7 +785,6 @@ int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
     prm.blur = p.blur; prm.sparse = p.sparse; prm.out = p.out;
     prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = p.iters; prm.norm_abs = p.norm_abs;
     prm.n_strips = plan.n_strips;
-    prm.zero = 0;
     prm.n_tasks = (int)((long)p.B * p.C * plan.n_strips);
     for (int i = 0; i < kMaxStrips; ++i) {
         prm.tile_x0[i] = i < plan.n_strips ? plan.tile_x0[i] : 0;
