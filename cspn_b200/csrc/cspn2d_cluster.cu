@@ -397,40 +397,30 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
     bool first = true;
-    // blur / sparse of a task: straight from global (aligned, read once; the previous task prefetched the lines into L2).
-    // They are requested one task ahead -- before the epilogue of the running task -- so their latency hides behind its
-    // stores and the task-boundary barrier.  W % 4 == 0 and the column % 4 == 0: a float4 is entirely inside or outside.
-    float4 dv_next[PR], sv_next[PR];
-    auto request_inputs = [&](int t) {
-        const int strip_t = t % prm.n_strips, bc_t = t / prm.n_strips;
-        const int xt = prm.tile_x0[strip_t] + lane * PC;
-        const float* bl = prm.blur + (size_t)bc_t * HW;
-        const float* sp = prm.sparse ? prm.sparse + (size_t)(bc_t / prm.C) * HW : nullptr;
-#pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            const int y = y_thr + r;
-            dv_next[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            sv_next[r] = dv_next[r];
-            if (xt >= 0 && xt < W && y < H) {
-                dv_next[r] = __ldg(reinterpret_cast<const float4*>(bl + (size_t)y * W + xt));
-                if (sp) sv_next[r] = __ldg(reinterpret_cast<const float4*>(sp + (size_t)y * W + xt));
-            }
-        }
-    };
-    if (task < n_tasks) request_inputs(task);
     for (; task < n_tasks; task += task_stride) {
         const int strip = task % prm.n_strips;
         const int bc = task / prm.n_strips;  // b*C + c
+        const int b = bc / prm.C;
         const int tile_x0 = prm.tile_x0[strip];
         const int x_thr = tile_x0 + lane * PC;  // first column of this thread
 
         // ---- thread state ---------------------------------------------------------------------------
         float w[PR][PC][8], d[PR][PC];
+        const float* blur = prm.blur + (size_t)bc * HW;
+        const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
+
+        // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2).
+        // W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
         const bool col_in = (x_thr >= 0) && (x_thr < W);
         float m[PR][PC];
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
-            const float4 dv = dv_next[r], sv = sv_next[r];
+            const int y = y_thr + r;
+            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), sv = dv;
+            if (col_in && y < H) {
+                dv = __ldg(reinterpret_cast<const float4*>(blur + (size_t)y * W + x_thr));
+                if (sparse) sv = __ldg(reinterpret_cast<const float4*>(sparse + (size_t)y * W + x_thr));
+            }
             d[r][0] = dv.x; d[r][1] = dv.y; d[r][2] = dv.z; d[r][3] = dv.w;
             m[r][0] = signf(sv.x); m[r][1] = signf(sv.y); m[r][2] = signf(sv.z); m[r][3] = signf(sv.w);
         }
@@ -553,9 +543,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
                 for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
         }
-
-        // the next task's blur / sparse are requested now: their latency overlaps the stores and barrier below
-        if (next < n_tasks) request_inputs(next);
 
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
