@@ -69,6 +69,54 @@ step3d_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const 
     dst[(size_t)c * V + p] = acc;
 }
 
+// Vectorised step for W % 4 == 0: one thread produces 4 consecutive voxels of a row.  The 27 weight planes stream
+// through as LDG.128 (they are the HBM traffic of this path: 108 B per voxel and step), the 9 neighbouring rows of the
+// current volume are read as one aligned float4 plus two edge scalars each (L1/L2 hits).
+__global__ void __launch_bounds__(128)
+step3d_vec4_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const float* __restrict__ cur,
+                   float* __restrict__ dst, int D, int H, int W) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z % D, c = blockIdx.z / D;
+    if (x >= W || y >= H) return;
+    const size_t HW = (size_t)H * W, V = (size_t)D * HW;
+    const size_t p = (size_t)z * HW + (size_t)y * W + x;
+    const float* cc = cur + (size_t)c * V;
+    // rows[dz+1][dy+1][0..5] = cur(z+dz, y+dy, x-1 .. x+4), zero outside the volume
+    float rows[3][3][6];
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int zz = z + dz, yy = y + dy;
+            float* r = rows[dz + 1][dy + 1];
+            if (zz >= 0 && zz < D && yy >= 0 && yy < H) {
+                const float* src = cc + (size_t)zz * HW + (size_t)yy * W + x;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w;
+                r[0] = x > 0 ? __ldg(src - 1) : 0.f;
+                r[5] = x + 4 < W ? __ldg(src + 4) : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) r[i] = 0.f;
+            }
+        }
+    const float4 kap = __ldg(reinterpret_cast<const float4*>(wk + 26 * V + p));
+    const float4 dz0 = __ldg(reinterpret_cast<const float4*>(d0 + (size_t)c * V + p));
+    float acc[4] = {kap.x * dz0.x, kap.y * dz0.y, kap.z * dz0.z, kap.w * dz0.w};
+#pragma unroll
+    for (int k = 0; k < 26; ++k) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wk + k * V + p));
+        const float* r = rows[off3_dz(k) + 1][off3_dy(k) + 1];
+        const int o = 1 + off3_dx(k);
+        acc[0] = fmaf(w.x, r[o], acc[0]);
+        acc[1] = fmaf(w.y, r[o + 1], acc[1]);
+        acc[2] = fmaf(w.z, r[o + 2], acc[2]);
+        acc[3] = fmaf(w.w, r[o + 3], acc[3]);
+    }
+    *reinterpret_cast<float4*>(dst + (size_t)c * V + p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 }  // namespace
 
 size_t generic3d_workspace_bytes(int B, int C, int D, int H, int W, int iters) {
@@ -105,8 +153,13 @@ int generic3d_forward(const float* guidance, const float* feat, float* out, int 
         ++*launches;
         const float* cur = d0;
         float* dst = (iters & 1) ? o : tmp;
+        const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out) |
+                                              reinterpret_cast<uintptr_t>(ws)) % 16 == 0);
         for (int it = 0; it < iters; ++it) {
-            step3d_kernel<<<dim3(g2.x, g2.y, D * C), block, 0, stream>>>(wk, d0, cur, dst, D, H, W);
+            if (vec4)
+                step3d_vec4_kernel<<<dim3((W / 4 + 31) / 32, (H + 3) / 4, D * C), dim3(32, 4), 0, stream>>>(wk, d0, cur, dst, D, H, W);
+            else
+                step3d_kernel<<<dim3(g2.x, g2.y, D * C), block, 0, stream>>>(wk, d0, cur, dst, D, H, W);
             ++*launches;
             cur = dst;
             dst = (dst == o) ? tmp : o;
