@@ -239,37 +239,35 @@ __device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)
 struct Xch {
     float* base;          // xch + lane*PC (parity 0, slot 0)
     uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
-    uint32_t rx_bytes;    // bytes that land in this CTA's exchange buffer per exchange (own rows + halo rows)
-    uint32_t self_data, self_bar;   // shared::cluster aliases of this CTA's own slot 0 (at my lane's columns) and full[0]
+    uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
     uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
     uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
     bool has_up, has_dn;
     // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
-    // above exists; remote_dn likewise; sig_tx = the one thread of the CTA that arms the tx count of each exchange
-    bool remote_up, remote_dn, sig_tx;
+    // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
+    bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
-// Publish the boundary rows of the new d into exchange buffer PAR: into this CTA's own slots and into the neighbour
-// CTAs' halo slots.  EVERY row store -- local ones included -- is an st.async whose bytes complete on the consumer's
-// mbarrier (complete_tx): the data carries its own "ready" signal, so there is no __syncwarp, no release fence and no
-// per-warp arrive on the critical path; one thread per CTA arms the expected byte count once per exchange.
+// Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
+// halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
 template <int PR, int PC, int NW, int PAR>
 __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
     using K = Cfg<PR, PC, NW>;
-    const uint32_t par_off = PAR * (uint32_t)K::kXchParityBytes;
-    const uint32_t own = x.self_data + par_off + (uint32_t)((1 + 2 * wy) * K::TW * sizeof(float));
-    const uint32_t own_bar = x.self_bar + 8 * PAR;
-    store_row_remote(own, top, own_bar);
-    store_row_remote(own + (uint32_t)(K::TW * sizeof(float)), bot, own_bar);
+    float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
+    store_row_smem(p + (1 + 2 * wy) * K::TW, top);
+    store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
+    const uint32_t bar = x.bar_full0 + 8 * PAR;
     // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
     // (remote_up / remote_dn are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform
     // branches, not divergence regions)
-    if (x.remote_up) store_row_remote(x.up_data + par_off, top, x.up_bar + 8 * PAR);
-    if (x.remote_dn) store_row_remote(x.dn_data + par_off, bot, x.dn_bar + 8 * PAR);
-    mbar_arrive_expect_tx_if(x.bar_full0 + 8 * PAR, x.rx_bytes, x.sig_tx);
+    if (x.remote_up) store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
+    if (x.remote_dn) store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
+    __syncwarp();
+    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
+    mbar_arrive_if(bar, x.sig);
 }
 
 // One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
@@ -351,12 +349,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
     xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
     xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
-    xc.rx_bytes = (uint32_t)(2 * NW + (xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
-    xc.self_data = map_to_cta(smem_u32(xc.base), crank);
-    xc.self_bar = map_to_cta(bar_full0, crank);
+    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
     xc.remote_up = xc.has_up && wy == 0;
     xc.remote_dn = xc.has_dn && wy == NW - 1;
-    xc.sig_tx = tid == 0;
+    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
+    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
@@ -380,8 +377,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        mbar_init(bar_full0, 1);        // one arrival (the arming thread) + the bytes of all row stores
-        mbar_init(bar_full0 + 8, 1);
+        mbar_init(bar_full0, NW);
+        mbar_init(bar_full0 + 8, NW);
         fence_barrier_init();
         fence_proxy_async();
         if (task < n_tasks) issue_stage(task);
