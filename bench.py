@@ -44,7 +44,7 @@ def recorded_traffic(algo_name):
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml, 50 ms period)."""
+    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml, ~2 ms period)."""
     REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
                0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
                0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
@@ -72,7 +72,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.nv:
