@@ -284,18 +284,16 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
                                         float (&eout)[PR][2]) {
     using K = Cfg<PR, PC, NW>;
-    // ---- before the wait: every own source row is scattered into the (pre-seeded) accumulators ---------------
-#pragma unroll
-    for (int rs = 0; rs < PR; ++rs) {
-        const Row<PC> src{din[rs], ein[rs]};
-        if (rs >= 1) scatter_row<PC, +1>(w[rs - 1], src, dout[rs - 1]);      // source is the row below row rs-1
-        scatter_row<PC, 0>(w[rs], src, dout[rs]);
-        if (rs + 1 < PR) scatter_row<PC, -1>(w[rs + 1], src, dout[rs + 1]);  // source is the row above row rs+1
+    // ---- before the wait: the own-source taps of the two BOUNDARY rows (they gate the publish) -----------------
+    {
+        const Row<PC> r0{din[0], ein[0]}, r1{din[1], ein[1]}, rp{din[PR - 2], ein[PR - 2]}, rl{din[PR - 1], ein[PR - 1]};
+        scatter_row<PC, 0>(w[0], r0, dout[0]);
+        scatter_row<PC, +1>(w[0], r1, dout[0]);
+        scatter_row<PC, 0>(w[PR - 1], rl, dout[PR - 1]);
+        scatter_row<PC, -1>(w[PR - 1], rp, dout[PR - 1]);
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
 #ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
-    // (ptxas issues the try_wait early and only branches on its result here, after part of the scatter phase; forcing
-    // it later through a data dependency measured slower: 427 vs 408 us on the 32x1216x352 workload.)
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
 #endif
     {
@@ -307,6 +305,14 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
         row_edges<PC>(d, de, x.first_lane, x.last_lane);
         scatter_row<PC, -1>(w[0], Row<PC>{u, ue}, dout[0]);
         scatter_row<PC, +1>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1]);
+    }
+    // ---- interior rows: independent of the exchange; placed here so that their FMAs fill the latency of the
+    // load -> shuffle -> select -> FMA chain above instead of leaving the sub-partition idle behind the barrier
+#pragma unroll
+    for (int r = 1; r <= PR - 2; ++r) {
+        scatter_row<PC, -1>(w[r], Row<PC>{din[r - 1], ein[r - 1]}, dout[r]);
+        scatter_row<PC, 0>(w[r], Row<PC>{din[r], ein[r]}, dout[r]);
+        scatter_row<PC, +1>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r]);
     }
     if constexpr (PUBLISH) {
 #ifndef CSPN_ABLATE_NO_SYNC
