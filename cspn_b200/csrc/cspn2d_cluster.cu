@@ -84,18 +84,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// step-counter flags in shared memory (producer: one release store after its row stores; consumer: acquire poll)
-__device__ __forceinline__ void flag_publish2(uint32_t addr, uint32_t step, bool pred) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.release.cta.shared::cta.v2.u32 [%0], {%1, %1};\n}\n" ::"r"(addr), "r"(step),
-                 "r"((int)pred)
-                 : "memory");
-}
-__device__ __forceinline__ void flag_wait(uint32_t addr, uint32_t step) {
-    uint32_t v;
-    do {
-        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    } while ((int)(v - step) < 0);
-}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -177,9 +165,7 @@ struct Cfg {
     // the folded constant term c' (one float per pixel) lives in shared memory: it is read once per pixel and
     // iteration (one LDS.128 per patch row), which frees PR*PC registers per thread
     static constexpr size_t kCBytes = (size_t)RB * TW * sizeof(float);
-    // sync words: mbarriers [tma, halo_up[2], halo_dn[2]] then one step-counter flag per exchange slot
-    static constexpr size_t kSyncBytes = 64 + 4 * ((kSlots + 1 + 3) & ~3);
-    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + kSyncBytes;
+    static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 64;
     static_assert(PC == 4, "vectorised global/shared accesses below assume 4 columns per thread");
     static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
@@ -250,43 +236,38 @@ __device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)
 }
 
 // Per-thread constants of the row exchange.
-// Inside a CTA the exchange is synchronised pairwise with step-counter flags (slot s carries the number of the last
-// step whose row was stored there): a warp waits only for the producers of the two rows it reads.  Rows that come from
-// a neighbour CTA arrive by st.async and complete on a per-halo mbarrier armed by the consuming warp.
 struct Xch {
     float* base;          // xch + lane*PC (parity 0, slot 0)
-    uint32_t flag0;       // shared address of flag[slot 0]
-    uint32_t bar_up0, bar_dn0;  // mbarriers of the halo rows from the CTA above / below, parity 0 (+8: parity 1)
+    uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
+    uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
     // shared::cluster addresses in the neighbour CTAs (parity 0; parity 1 is a constant offset away)
-    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its bar_dn0
-    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its bar_up0
-    // roles: remote_* = this warp owns the CTA's top / bottom row and the neighbour CTA exists (it sends the row over
-    // DSMEM and, as the consumer of the opposite halo row, arms that row's byte count); sig = lane 0
-    bool remote_up, remote_dn, sig;
-    bool local_up, local_dn;    // the row above / below my patch is produced by a warp of this CTA
+    uint32_t up_data, up_bar;   // CTA above: its last slot ("halo from below") at my lane's columns, its full[0]
+    uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
+    bool has_up, has_dn;
+    // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
+    // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
+    bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
 };
 
-// Publish the boundary rows of the new d (the result of step number `step`) into exchange buffer PAR.
+// Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
+// halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
 template <int PR, int PC, int NW, int PAR>
-__device__ __forceinline__ void publish(const Xch& x, int wy, uint32_t step, const float (&top)[PC], const float (&bot)[PC]) {
+__device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
     using K = Cfg<PR, PC, NW>;
     float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
     store_row_smem(p + (1 + 2 * wy) * K::TW, top);
     store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
+    const uint32_t bar = x.bar_full0 + 8 * PAR;
     // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
-    // (remote_* are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform branches)
-    if (x.remote_up) {
-        store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
-        mbar_arrive_expect_tx_if(x.bar_up0 + 8 * PAR, K::TW * 4, x.sig);   // and I expect its row for the same step
-    }
-    if (x.remote_dn) {
-        store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
-        mbar_arrive_expect_tx_if(x.bar_dn0 + 8 * PAR, K::TW * 4, x.sig);
-    }
+    // (remote_up / remote_dn are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform
+    // branches, not divergence regions)
+    if (x.remote_up) store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
+    if (x.remote_dn) store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
     __syncwarp();
-    flag_publish2(x.flag0 + 4 * (1 + 2 * wy), step, x.sig);   // flags of my top and bottom slot (adjacent words)
+    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
+    mbar_arrive_if(bar, x.sig);
 }
 
 // One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
@@ -299,7 +280,7 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, uint32_t step, con
 // rows), then the new boundary rows are published at once and the x-edges of the new rows (shuffles) are computed in
 // the tail, off the critical path of the other warps.
 template <int PR, int PC, int NW, int PAR, bool PUBLISH>
-__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t step, uint32_t phase, const float (&w)[PR][PC][8],
+__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
                                         float (&eout)[PR][2]) {
     using K = Cfg<PR, PC, NW>;
@@ -312,12 +293,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t step, uin
         scatter_row<PC, -1>(w[PR - 1], rp, dout[PR - 1]);
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
-    // rows of step `step` (the input of this step): from a warp of this CTA -> its flag; from a neighbour CTA -> the
-    // halo mbarrier; outside the image -> nothing to wait for (the slot stays zero)
-    if (x.local_up) flag_wait(x.flag0 + 4 * (2 * wy), step);
-    else if (x.remote_up) mbar_wait(x.bar_up0 + 8 * PAR, phase);
-    if (x.local_dn) flag_wait(x.flag0 + 4 * (2 * wy + 3), step);
-    else if (x.remote_dn) mbar_wait(x.bar_dn0 + 8 * PAR, phase);
+#ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+#endif
     {
         const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
         float u[PC], ue[2], d[PC], de[2];
@@ -337,7 +315,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t step, uin
         scatter_row<PC, +1>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r]);
     }
     if constexpr (PUBLISH) {
-        publish<PR, PC, NW, PAR ^ 1>(x, wy, step + 1, dout[0], dout[PR - 1]);
+#ifndef CSPN_ABLATE_NO_SYNC
+        publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+#endif
         // ---- tail: seed the next step's accumulators, x-edges of the new rows ---------------------------------
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
@@ -356,9 +336,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
     float* cbuf = reinterpret_cast<float*>(smem_raw + K::kStageBytes + K::kXchBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes + K::kCBytes);
-    // bars[0] tma, [1..2] halo row from the CTA above (parity 0/1), [3..4] halo row from the CTA below; then the flags
-    const uint32_t bar_tma = smem_u32(bars), bar_up0 = smem_u32(bars + 1), bar_dn0 = smem_u32(bars + 3);
-    uint32_t* flags = reinterpret_cast<uint32_t*>(bars + 8) + 1;   // +1: flag[1] (a warp's top slot) is 8-byte aligned for the v2 store
+    const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int wy = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform for the compiler
@@ -368,21 +346,20 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const int y_thr = band_y0 + wy * PR;    // first row of this thread
     const size_t HW = (size_t)H * W;
 
-    const bool has_up = crank > 0, has_dn = crank + 1 < csize;
     Xch xc;
     xc.base = xch + lane * PC;
-    xc.flag0 = smem_u32(flags);
-    xc.bar_up0 = bar_up0;
-    xc.bar_dn0 = bar_dn0;
-    xc.up_data = has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
-    xc.up_bar = has_up ? map_to_cta(bar_dn0, crank - 1) : 0u;     // my top row is the upper CTA's halo-from-below
-    xc.dn_data = has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
-    xc.dn_bar = has_dn ? map_to_cta(bar_up0, crank + 1) : 0u;     // my bottom row is the lower CTA's halo-from-above
-    xc.remote_up = has_up && wy == 0;
-    xc.remote_dn = has_dn && wy == NW - 1;
-    xc.sig = lane == 0;
-    xc.local_up = wy > 0;
-    xc.local_dn = wy < NW - 1;
+    xc.bar_full0 = bar_full0;
+    xc.has_up = crank > 0;
+    xc.has_dn = crank + 1 < csize;
+    xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
+    xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
+    xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
+    xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
+    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
+    xc.remote_up = xc.has_up && wy == 0;
+    xc.remote_dn = xc.has_dn && wy == NW - 1;
+    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
+    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
@@ -406,8 +383,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        for (int i = 0; i < 4; ++i) mbar_init(bar_up0 + 8 * i, 1);   // armed by the one consuming lane, completed by tx
-        for (int i = 0; i < K::kSlots; ++i) flags[i] = 0u;
+        mbar_init(bar_full0, NW);
+        mbar_init(bar_full0 + 8, NW);
         fence_barrier_init();
         fence_proxy_async();
         if (task < n_tasks) issue_stage(task);
@@ -415,16 +392,15 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     // every CTA's barriers must be initialised before a neighbour's st.async can target them
     cluster_arrive();
     // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
-    if (!has_up)
+    if (!xc.has_up)
         for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
-    if (!has_dn)
+    if (!xc.has_dn)
         for (int i = tid; i < TW; i += K::kThreads) {
             xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
             xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
         }
     cluster_wait();
 
-    uint32_t gstep = 0;   // number of exchange steps published so far by every warp of the cluster (flags carry it)
     uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
@@ -541,8 +517,9 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
         first = false;
         const int iters = prm.iters;
-        ++gstep;
-        publish<PR, PC, NW, 0>(xc, wy, gstep, d[0], d[PR - 1]);
+#ifndef CSPN_ABLATE_NO_SYNC
+        publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+#endif
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
@@ -551,18 +528,18 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         for (int r = 0; r < PR; ++r) load_row_smem(xc.cbuf + r * TW, d2[r]);   // accumulators of the first step start from c'
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
-            iterate<PR, PC, NW, 0, true>(xc, wy, gstep, ph0, w, d, e, d2, e2);
-            ph0 ^= 1; ++gstep;
-            iterate<PR, PC, NW, 1, true>(xc, wy, gstep, ph1, w, d2, e2, d, e);
-            ph1 ^= 1; ++gstep;
+            iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            ph0 ^= 1;
+            iterate<PR, PC, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
+            ph1 ^= 1;
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
-            iterate<PR, PC, NW, 0, true>(xc, wy, gstep, ph0, w, d, e, d2, e2);
-            ph0 ^= 1; ++gstep;
-            iterate<PR, PC, NW, 1, false>(xc, wy, gstep, ph1, w, d2, e2, d, e);
+            iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            ph0 ^= 1;
+            iterate<PR, PC, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         } else if (iters - it == 1) {
-            iterate<PR, PC, NW, 0, false>(xc, wy, gstep, ph0, w, d, e, d2, e2);
+            iterate<PR, PC, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
         }
         cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
