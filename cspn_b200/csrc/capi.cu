@@ -188,6 +188,8 @@ struct Slot {
 struct HostPipe {
     std::mutex mu;
     Slot slots[3];
+    Slot result;          // whole-batch output on the device + the stream of the single D2H at the end
+    cudaEvent_t done[3] = {nullptr, nullptr, nullptr};
     int device = -1;
 };
 HostPipe g_pipes[16];
@@ -238,7 +240,15 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
     const size_t d_bytes = align_up((size_t)nb * C * HW * sizeof(float), 256);
     const size_t s_bytes = sparse ? align_up((size_t)nb * HW * sizeof(float), 256) : 0;
     const size_t ws_bytes = align_up(cspn2d_workspace_bytes(nb, C, H, W, iters, algo), 256);
-    const size_t slot_bytes = g_bytes + 2 * d_bytes + s_bytes + ws_bytes;
+    const size_t slot_bytes = g_bytes + d_bytes + s_bytes + ws_bytes;
+    // Results stay on the device until every chunk has been uploaded: on this platform an H2D and a D2H running
+    // concurrently each drop from 48-55 GB/s to 38 GB/s, and the output is only 1/10 of the input, so one D2H at the
+    // end (1 ms) beats overlapping it (measured: 17.8 ms -> see profiles/).
+    rc = ensure_slot(pipe.result, (size_t)B * C * HW * sizeof(float));
+    if (rc != CSPN_OK) return rc;
+    float* dout_all = reinterpret_cast<float*>(pipe.result.buf);
+    for (auto& e : pipe.done)
+        if (!e) CSPN_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int launches = 0, chunk = 0;
     for (int b0 = 0; b0 < B; b0 += nb, ++chunk) {
         Slot& s = pipe.slots[chunk % 3];
@@ -247,9 +257,8 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
         const int n = (B - b0 < nb) ? B - b0 : nb;
         float* dg = reinterpret_cast<float*>(s.buf);
         float* dd = reinterpret_cast<float*>(s.buf + g_bytes);
-        float* dout = reinterpret_cast<float*>(s.buf + g_bytes + d_bytes);
-        float* dsp = sparse ? reinterpret_cast<float*>(s.buf + g_bytes + 2 * d_bytes) : nullptr;
-        void* dws = ws_bytes ? s.buf + g_bytes + 2 * d_bytes + s_bytes : nullptr;
+        float* dsp = sparse ? reinterpret_cast<float*>(s.buf + g_bytes + d_bytes) : nullptr;
+        void* dws = ws_bytes ? s.buf + g_bytes + d_bytes + s_bytes : nullptr;
         // only channels 0..7 of the guidance are used (cspn.py:91-98): copy just those planes.  (A pitched 2D copy
         // runs at ~20 GB/s on this platform against 48 GB/s for a linear one, so it is used only when needed.)
         if (guidance_channels == 8)
@@ -264,15 +273,18 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
         if (sparse)
             CSPN_CUDA_TRY(cudaMemcpyAsync(dsp, sparse + (size_t)b0 * HW, (size_t)n * HW * sizeof(float),
                                           cudaMemcpyHostToDevice, s.stream));
-        rc = cspn2d_fwd_f32(dg, dd, dsp, dout, n, C, H, W, 8, iters, norm_type, algo, dws, ws_bytes,
+        rc = cspn2d_fwd_f32(dg, dd, dsp, dout_all + (size_t)b0 * C * HW, n, C, H, W, 8, iters, norm_type, algo, dws, ws_bytes,
                             (cspn_stream_t)s.stream);
         if (rc != CSPN_OK) return rc;
         launches += g_last_launches;
-        CSPN_CUDA_TRY(cudaMemcpyAsync(out + (size_t)b0 * C * HW, dout, (size_t)n * C * HW * sizeof(float),
-                                      cudaMemcpyDeviceToHost, s.stream));
     }
-    for (auto& s : pipe.slots)
-        if (s.stream) CSPN_CUDA_TRY(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < 3; ++i)
+        if (pipe.slots[i].stream) {
+            CSPN_CUDA_TRY(cudaEventRecord(pipe.done[i], pipe.slots[i].stream));
+            CSPN_CUDA_TRY(cudaStreamWaitEvent(pipe.result.stream, pipe.done[i], 0));
+        }
+    CSPN_CUDA_TRY(cudaMemcpyAsync(out, dout_all, (size_t)B * C * HW * sizeof(float), cudaMemcpyDeviceToHost, pipe.result.stream));
+    CSPN_CUDA_TRY(cudaStreamSynchronize(pipe.result.stream));
     g_last_launches = launches;
     return CSPN_OK;
 }
