@@ -249,9 +249,11 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
     float* dout_all = reinterpret_cast<float*>(pipe.result.buf);
     for (auto& e : pipe.done)
         if (!e) CSPN_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const char* ns_env = getenv("CSPN_B200_HOST_STREAMS");   // developer hook for tuning runs
+    const int nslots = ns_env && atoi(ns_env) >= 1 && atoi(ns_env) <= 3 ? atoi(ns_env) : 3;
     int launches = 0, chunk = 0;
     for (int b0 = 0; b0 < B; b0 += nb, ++chunk) {
-        Slot& s = pipe.slots[chunk % 3];
+        Slot& s = pipe.slots[chunk % nslots];
         rc = ensure_slot(s, slot_bytes);
         if (rc != CSPN_OK) return rc;
         const int n = (B - b0 < nb) ? B - b0 : nb;
