@@ -145,16 +145,20 @@ def cpu_baseline_leg():
     g, d, s = make_inputs(0, 8, 1, H, W)
     gn, dn, sn = g.numpy(), d.numpy(), s.numpy()
     ncpu = os.cpu_count() or 1
-    c_oracle.cspn2d(gn[:1], dn[:1], sn[:1], ITERS, NORM, nthreads=ncpu)
-    t0 = time.perf_counter()
-    c_oracle.cspn2d(gn, dn, sn, ITERS, NORM, nthreads=ncpu)
-    c_mpx = 8 * H * W / (time.perf_counter() - t0) / 1e6
+    c_mpx, c_thr = 0.0, 1
+    for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):      # the OpenMP port also has a sweet spot
+        c_oracle.cspn2d(gn[:1], dn[:1], sn[:1], ITERS, NORM, nthreads=nt)
+        t0 = time.perf_counter()
+        c_oracle.cspn2d(gn, dn, sn, ITERS, NORM, nthreads=nt)
+        r = 8 * H * W / (time.perf_counter() - t0) / 1e6
+        if r > c_mpx:
+            c_mpx, c_thr = r, nt
     return {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'cores': threads, 'kind': 'port',
             'sample': f'{nb}x{W}x{H} images, {ITERS} iters, 1 warm-up + 2 timed forwards of oracle/cspn_torch_port.py '
                       f'(the reference op sequence of cspn.py:42-83 on CPU; /root/reference is absent on this box); '
                       f'{threads} torch threads = the fastest of 4..{os.cpu_count()} on this host',
             'host_cpus': os.cpu_count(),
-            'c_openmp_port_mpx_s': round(c_mpx, 3), 'c_openmp_threads': ncpu}
+            'c_openmp_port_mpx_s': round(c_mpx, 3), 'c_openmp_threads': c_thr}
 
 
 def run_reference_arm(args):
