@@ -225,6 +225,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # keep stdout to the single JSON line: NCCL's version banner / debug log goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     algo = {'auto': _lib.ALGO_AUTO, 'generic': _lib.ALGO_GENERIC, 'cluster': _lib.ALGO_CLUSTER}[args.algo]
