@@ -183,12 +183,30 @@ def run_reference_arm(args):
         'e2e': {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner comes from C code)
+    is diverted to stderr for the duration of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + '\n').encode())
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -201,6 +219,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    quiet_stdout()
 
     if args.impl == 'reference':
         run_reference_arm(args)
@@ -344,7 +363,7 @@ def main():
         }
         if gather:
             line['gather'] = gather
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
