@@ -12,22 +12,23 @@
 //   cluster  = one task.  The CS CTAs of a thread-block cluster stack along y; CTA r owns the band of
 //              RB = NW*PR rows starting at r*RB.  (CS*RB >= H.)
 //   CTA      = NW warps stacked along y; warp wy owns PR rows; lane l owns PC consecutive columns.
-//   thread   = a PR x PC pixel patch whose ENTIRE state lives in registers for all N iterations:
-//              8 folded weights + the constant term + the current value per pixel (10 registers/pixel).
+//   thread   = a PR x PC pixel patch whose state lives in registers for all N iterations: 8 folded weights and
+//              the current value per pixel (two value sets alternate as input / output of a step); the constant
+//              term c' is read from shared memory once per step.
 // Data movement
-//   * the 8 guidance planes arrive by TMA (cp.async.bulk.tensor.3d), one box per channel whose origin is
-//     shifted by that channel's (dy,dx): the box lands in shared memory as the GATHERED affinity a_k
-//     (cspn.py:105-132), and TMA's out-of-bounds zero fill is exactly ZeroPad2d;
+//   * the 8 guidance planes arrive by TMA (cp.async.bulk.tensor.3d), one box per channel whose origin is shifted
+//     by that channel's dy: the ROW gather of cspn.py:105-132 is free and TMA's out-of-bounds zero fill is exactly
+//     ZeroPad2d.  The column shift (dx = +-1) cannot ride on the box origin -- TMA needs a 16-byte aligned
+//     innermost coordinate -- so boxes carry a 4-column apron and the shift is a shuffle in the prologue;
+//   * clusters are persistent: the next task's boxes are issued as soon as the prologue has consumed the staging
+//     buffer, so HBM streams while the current task iterates in registers;
 //   * blur depth / sparse depth are read once with vectorised global loads, the result is written once;
-//   * per iteration, x-neighbours come from warp shuffles, y-neighbours inside a thread from its own
-//     registers, across warps from a double-buffered shared-memory row exchange, and across CTAs of the
-//     cluster from the same exchange buffers written remotely through DSMEM with st.async, whose
-//     complete_tx lands on the consumer's mbarrier: pure dataflow, one mbarrier wait per iteration and no
-//     cluster-wide barrier inside the loop.  Boundary rows of each patch are computed and published first,
-//     so the DSMEM latency hides behind the interior rows.
-// No tensor cores: a 9-point stencil with per-pixel weights is FMA + HBM bound, not a contraction.
-#include <cooperative_groups.h>
-
+//   * per iteration, x-neighbours come from warp shuffles, y-neighbours inside a thread from its own registers,
+//     across warps from a double-buffered shared-memory row exchange, and across CTAs of the cluster from the same
+//     exchange buffers written remotely through DSMEM with st.async, whose complete_tx lands on the consumer's
+//     mbarrier: pure dataflow, one mbarrier wait per iteration and no cluster-wide barrier inside the loop.
+// No tensor cores: a 9-point stencil with per-pixel weights is FMA-issue + HBM bound, not a contraction.
+// Tuning history and the measured dead ends (FFMA2, pairwise barriers, flags, ...): profiles/r01_tuning_log.md.
 #include <cstdlib>
 #include <mutex>
 #include <vector>
