@@ -153,7 +153,25 @@ def cpu_baseline_leg():
         r = 8 * H * W / (time.perf_counter() - t0) / 1e6
         if r > c_mpx:
             c_mpx, c_thr = r, nt
+    # for context only: the same reference op sequence run eagerly on this GPU (the reference's native mode:
+    # ~700 library-kernel launches per forward), 4 images
+    gpu_eager = None
+    try:
+        from oracle import cspn_torch_port as tp
+        if torch.cuda.is_available():
+            gg, dd, ss = [t[:4].cuda() for t in (g, d, s)]
+            with torch.no_grad():
+                tp.cspn2d_torch(gg, dd, ss, ITERS, NORM)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    tp.cspn2d_torch(gg, dd, ss, ITERS, NORM)
+                torch.cuda.synchronize()
+            gpu_eager = round(3 * 4 * H * W / (time.perf_counter() - t0) / 1e6, 1)
+    except Exception:
+        gpu_eager = None
     return {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'cores': threads, 'kind': 'port',
+            'reference_ops_eager_on_this_gpu_mpx_s': gpu_eager,
             'sample': f'{nb}x{W}x{H} images, {ITERS} iters, 1 warm-up + 2 timed forwards of oracle/cspn_torch_port.py '
                       f'(the reference op sequence of cspn.py:42-83 on CPU; /root/reference is absent on this box); '
                       f'{threads} torch threads = the fastest of 4..{os.cpu_count()} on this host',
