@@ -592,6 +592,7 @@ const std::vector<KernelCfg>& configs() {
         make_cfg<4, 4, 8>(),   // 32 x 128
         make_cfg<3, 4, 8>(),   // 24 x 128
         make_cfg<2, 4, 8>(),   // 16 x 128 (small images)
+        make_cfg<5, 4, 4>(),   // 20 x 128 with 4 warps: two CTAs (of different tasks) fit one SM and de-phase each other
     };
     return v;
 }
