@@ -175,6 +175,35 @@ def propagate3d(guidance, feat, prop_time=12, norm_type='26sum_abs'):
     return out
 
 
+class _Propagate3dFn(torch.autograd.Function):
+    """autograd seam of the 3D operator (the Paddle op is trained through: cspn_paddle/demo.py:72-75)."""
+
+    @staticmethod
+    def forward(ctx, guidance, feat, prop_time, norm_type):
+        ctx.save_for_backward(guidance, feat)
+        ctx.cfg = (prop_time, norm_type)
+        return propagate3d(guidance, feat, prop_time, norm_type)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        guidance, feat = ctx.saved_tensors
+        prop_time, norm_type = ctx.cfg
+        if not grad_out.is_cuda:
+            raise _lib.CspnError('backward needs CUDA tensors')
+        L = _lib.lib()
+        B, C, D, H, W = feat.shape
+        g, f, go = guidance.contiguous(), feat.contiguous(), grad_out.contiguous()
+        gg = torch.empty_like(g) if ctx.needs_input_grad[0] else None
+        gf = torch.empty_like(f) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(f.device):
+            ws_bytes = L.cspn3d_bwd_workspace_bytes(B, C, D, H, W, int(prop_time))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=f.device) if ws_bytes else None
+            rc = L.cspn3d_bwd_f32(_ptr(g), _ptr(f), _ptr(go), _ptr(gg), _ptr(gf), B, C, D, H, W, int(prop_time),
+                                  NORM3D[norm_type], _ptr(ws), ws_bytes, _stream(f.device))
+        _lib.check(rc, 'cspn3d_bwd_f32')
+        return gg, gf, None, None
+
+
 class Affinity_Propagate3D(nn.Module):
     """3D (3x3x3, 26 neighbours) counterpart; the reference has only call sites for it
     (cspn_paddle/demo.py:20-54: CSPN.cspn(guide, feat)).  norm_type:
@@ -190,5 +219,5 @@ class Affinity_Propagate3D(nn.Module):
 
     def forward(self, guidance, feat):
         if torch.is_grad_enabled() and (guidance.requires_grad or feat.requires_grad) and self.prop_time > 0:
-            raise NotImplementedError('3D backward is not implemented (DESIGN.md, "next")')
+            return _Propagate3dFn.apply(guidance, feat, self.prop_time, self.norm_type)
         return propagate3d(guidance, feat, self.prop_time, self.norm_type)

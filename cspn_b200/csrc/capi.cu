@@ -160,6 +160,28 @@ int cspn3d_fwd_f32(const float* guidance, const float* feat, float* out, int B, 
     return rc;
 }
 
+size_t cspn3d_bwd_workspace_bytes(int B, int C, int D, int H, int W, int iters) {
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || iters <= 0) return 0;
+    return bwd3d_workspace_bytes(C, D, H, W, iters);
+}
+
+int cspn3d_bwd_f32(const float* guidance, const float* feat, const float* grad_out, float* grad_guidance, float* grad_feat,
+                   int B, int C, int D, int H, int W, int iters, int norm_type, void* workspace, size_t workspace_bytes,
+                   cspn_stream_t stream) {
+    clear_error();
+    g_last_launches = 0;
+    if (!guidance || !feat || !grad_out) { set_error("null tensor pointer"); return CSPN_ERR_INVALID_ARGUMENT; }
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0 || iters < 0) { set_error("invalid 3D shape / prop_step"); return CSPN_ERR_INVALID_ARGUMENT; }
+    if (norm_type < CSPN_NORM_26SUM || norm_type > CSPN_NORM_PADDLE) { set_error("unknown 3D norm_type %d", norm_type); return CSPN_ERR_INVALID_ARGUMENT; }
+    DeviceGuard guard(device_of(feat));
+    if (!guard.ok) { set_error("cannot select the device of `feat`"); return CSPN_ERR_CUDA; }
+    int launches = 0;
+    int rc = bwd3d(guidance, feat, grad_out, grad_guidance, grad_feat, B, C, D, H, W, iters, norm_type, workspace, workspace_bytes,
+                   (cudaStream_t)stream, &launches);
+    g_last_launches = launches;
+    return rc;
+}
+
 int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int algo, char* buf, int buf_len) {
     if (!buf || buf_len <= 0) return 0;
     Problem2D p{nullptr, nullptr, nullptr, nullptr, B, C, H, W, 8, iters, 0};
@@ -175,8 +197,8 @@ int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int algo, char* 
 
 // ---- host-buffer pipeline -------------------------------------------------------------------
 // The reference-facing call with HOST buffers (bench.py "e2e"): batch chunks flow through three
-// slots, each with its own stream and device buffers, so chunk i's H2D, chunk i-1's kernel and
-// chunk i-2's D2H overlap on the two copy engines and the SMs.
+// slots, each with its own stream and device buffers, so chunk i's H2D overlaps chunk i-1's kernel;
+// results stay on the device and leave in one D2H at the end (see the comment in the 2D entry point).
 namespace cspn {
 namespace {
 

@@ -75,4 +75,8 @@ size_t generic3d_workspace_bytes(int B, int C, int D, int H, int W, int iters);
 int generic3d_forward(const float* guidance, const float* feat, float* out, int B, int C, int D, int H, int W,
                       int iters, int mode, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 
+size_t bwd3d_workspace_bytes(int C, int D, int H, int W, int iters);
+int bwd3d(const float* guidance, const float* feat, const float* grad_out, float* grad_guidance, float* grad_feat, int B, int C,
+          int D, int H, int W, int iters, int mode, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+
 }  // namespace cspn

@@ -107,6 +107,15 @@ CSPN_API int cspn3d_fwd_f32(const float* guidance, const float* feat, float* out
 CSPN_API int cspn3d_fwd_f32_host(const float* guidance, const float* feat, float* out,
                         int B, int C, int D, int H, int W, int iters, int norm_type, int device);
 
+/* ---- 3D backward (the Paddle op trains too: cspn_paddle/demo.py:72-75 minimises a loss through it).
+ * grad_guidance [B][26][D][H][W], grad_feat [B][C][D][H][W]; either may be NULL. */
+CSPN_API size_t cspn3d_bwd_workspace_bytes(int B, int C, int D, int H, int W, int iters);
+
+CSPN_API int cspn3d_bwd_f32(const float* guidance, const float* feat, const float* grad_out,
+                   float* grad_guidance, float* grad_feat,
+                   int B, int C, int D, int H, int W, int iters, int norm_type,
+                   void* workspace, size_t workspace_bytes, cspn_stream_t stream);
+
 /* ---- pinned host buffers for the *_host entry points ---------------------------------------- */
 CSPN_API void* cspn_host_alloc(size_t bytes); /* cudaHostAlloc; NULL on failure */
 CSPN_API void cspn_host_free(void* p);

@@ -45,3 +45,35 @@ def cspn2d_torch(guidance, blur_depth, sparse_depth=None, prop_time=24, norm_typ
         if mask is not None:
             result = (1 - mask) * result + mask * raw                        # :81
     return result
+
+
+# ---- 3D (differentiable restatement of oracle/cspn_numpy.py::cspn3d; used as the autograd reference in tests) ----
+OFFSETS_3D = tuple((1 - f, 1 - t, 1 - l) for f in range(3) for t in range(3) for l in range(3) if (f, t, l) != (1, 1, 1))
+
+
+def _shift3d(a, dz, dy, dx):
+    """b[..., z, y, x] = a[..., z+dz, y+dy, x+dx], zero outside."""
+    D, H, W = a.shape[-3:]
+    p = F.pad(a, (1, 1, 1, 1, 1, 1))
+    return p[..., 1 + dz:1 + dz + D, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+
+
+def cspn3d_torch(guidance, feat, prop_time=12, norm_type='26sum_abs'):
+    g = guidance[:, :26]
+    if norm_type == 'paddle':
+        a = g.abs()                                               # demo.py:24
+        gate = a / a.sum(1, keepdim=True)                         # demo.py:47-49 (own location)
+    else:
+        if 'abs' in norm_type:
+            g = g.abs()
+        a = torch.stack([_shift3d(g[:, k], *o) for k, o in enumerate(OFFSETS_3D)], 1)
+        gate = a / a.abs().sum(1, keepdim=True)
+    gate_sum = gate.sum(1, keepdim=True)
+    raw = feat
+    result = feat
+    for _ in range(prop_time):
+        acc = 0
+        for k, o in enumerate(OFFSETS_3D):
+            acc = acc + gate[:, k:k + 1] * _shift3d(result, *o)
+        result = acc if norm_type == 'paddle' else (1.0 - gate_sum) * raw + acc
+    return result

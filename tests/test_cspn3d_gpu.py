@@ -47,3 +47,25 @@ def test_3d_host_entry_point():
     a = cspn_b200.propagate3d(g, f, 5, 'paddle')
     b = cspn_b200.propagate3d(g.cuda(), f.cuda(), 5, 'paddle').cpu()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('mode', ['26sum', '26sum_abs', 'paddle'])
+@pytest.mark.parametrize('shape,n', [((2, 1, 4, 6, 8), 3), ((1, 2, 5, 5, 12), 4)])
+def test_3d_gradients_match_autograd_of_the_restatement(shape, n, mode):
+    from oracle import cspn_torch_port as tp
+    B, C, D, H, W = shape
+    g, f = make_inputs_3d(9, B, C, D, H, W, signed=(mode != 'paddle'))
+    g = g + 0.05 * torch.sign(g)                                   # keep |g| away from the kink of abs
+    go = torch.randn(B, C, D, H, W, generator=torch.Generator().manual_seed(2))
+    g64, f64 = g.double().requires_grad_(True), f.double().requires_grad_(True)
+    ref = tp.cspn3d_torch(g64, f64, n, mode)
+    assert np.allclose(ref.detach().numpy(), onp.cspn3d(g.numpy(), f.numpy(), n, mode, dtype=np.float64), rtol=1e-9, atol=1e-9)
+    ref.backward(go.double())
+    gc, fc = g.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+    out = cspn_b200.Affinity_Propagate3D(n, 3, mode)(gc, fc)
+    out.backward(go.cuda())
+    for ours, theirs, name in ((gc.grad, g64.grad, 'guidance'), (fc.grad, f64.grad, 'feat')):
+        ours = ours.double().cpu()
+        scale = theirs.abs().mean()
+        err = (ours - theirs).abs()
+        assert (err <= 2e-3 * (theirs.abs() + scale)).all(), (name, mode, float(err.max()), float(scale))
