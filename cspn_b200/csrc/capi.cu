@@ -85,11 +85,11 @@ void cspn_host_free(void* p) {
 
 size_t cspn2d_workspace_bytes(int B, int C, int H, int W, int iters, int algo) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || iters <= 0) return 0;
-    if (algo == CSPN_ALGO_CLUSTER) return 0;
-    if (algo == CSPN_ALGO_AUTO) {
+    if (algo != CSPN_ALGO_GENERIC) {
         Problem2D p{nullptr, nullptr, nullptr, nullptr, B, C, H, W, 8, iters, 0};
         char why[8];
-        if (cluster2d_supported(p, why, sizeof(why))) return 0;
+        if (cluster2d_supported(p, why, sizeof(why))) return cluster2d_workspace_bytes(B, C, H, W, iters);
+        if (algo == CSPN_ALGO_CLUSTER) return 0;   // the forward call will report why it is unsupported
     }
     return generic2d_workspace_bytes(B, C, H, W, iters);
 }
@@ -109,7 +109,7 @@ int cspn2d_fwd_f32(const float* guidance, const float* blur, const float* sparse
     if (chosen < 0) { set_error("cluster kernel unsupported for this problem: %s", why); return chosen; }
     g_last_algo = chosen;
     int launches = 0;
-    rc = (chosen == CSPN_ALGO_CLUSTER) ? cluster2d_forward(p, (cudaStream_t)stream, &launches)
+    rc = (chosen == CSPN_ALGO_CLUSTER) ? cluster2d_forward(p, workspace, workspace_bytes, (cudaStream_t)stream, &launches)
                                        : generic2d_forward(p, workspace, workspace_bytes, (cudaStream_t)stream, &launches);
     g_last_launches = launches;
     return rc;

@@ -59,7 +59,8 @@ size_t generic2d_workspace_bytes(int B, int C, int H, int W, int iters);
 int generic2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 
 bool cluster2d_supported(const Problem2D& p, char* why, int why_len);
-int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches);
+size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters);
+int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len);
 
 void launch_prep2d(const float* guidance, const float* sparse, float* wk, int B, int H, int W, int gch, int norm_abs,

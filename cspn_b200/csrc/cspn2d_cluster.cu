@@ -40,16 +40,22 @@ namespace cspn {
 namespace {
 
 constexpr int kMaxStrips = 40;
+constexpr int kMaxBands = 64;
+constexpr int kMaxPasses = 64;
 
 struct ClusterParams {
-    const float* blur;    // [B*C][H][W]
+    const float* blur;    // [B*C][H][W]  d_0: the constant term always comes from here (cspn.py:58,76,81)
+    const float* init;    // [B*C][H][W]  d at the start of this pass (null: d_0) -- passes after the first
     const float* sparse;  // [B][H][W] or null
     float* out;           // [B*C][H][W]
     int C, H, W, gch, iters, norm_abs;
-    int n_strips, n_tasks;
+    int n_strips, n_bands, n_tasks;
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
+    int band_y0[kMaxBands];   // first row of the cluster's row range (one band unless the image is taller than a cluster)
+    int uy0[kMaxBands];       // useful (stored) rows [uy0, uy1)
+    int uy1[kMaxBands];
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------
@@ -343,8 +349,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const int wy = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform for the compiler
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const int H = prm.H, W = prm.W;
-    const int band_y0 = (int)crank * RB;
-    const int y_thr = band_y0 + wy * PR;    // first row of this thread
+    const int cta_dy = (int)crank * RB;     // first row of this CTA / of this thread, relative to the task's band origin
+    const int thr_dy = cta_dy + wy * PR;
     const size_t HW = (size_t)H * W;
 
     Xch xc;
@@ -374,12 +380,14 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     // columns arrive as zeros (= ZeroPad2d, cspn.py:105-129).
     auto issue_stage = [&](int t) {
         const int strip_t = t % prm.n_strips;
-        const int b_t = (t / prm.n_strips) / prm.C;
+        const int q_t = t / prm.n_strips;
+        const int band_t = q_t % prm.n_bands;
+        const int b_t = (q_t / prm.n_bands) / prm.C;
         mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             tma_load_3d(smem_u32(stage) + (uint32_t)(k * K::kPlaneBytes), &tm_guidance, prm.tile_x0[strip_t] - 4,
-                        band_y0 + off2_dy(k), b_t * prm.gch + k, bar_tma);
+                        prm.band_y0[band_t] + cta_dy + off2_dy(k), b_t * prm.gch + k, bar_tma);
     };
 
     if (tid == 0) {
@@ -406,8 +414,10 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
         const int strip = task % prm.n_strips;
-        const int bc = task / prm.n_strips;  // b*C + c
+        const int band = (task / prm.n_strips) % prm.n_bands;
+        const int bc = (task / prm.n_strips) / prm.n_bands;  // b*C + c
         const int b = bc / prm.C;
+        const int y_thr = prm.band_y0[band] + thr_dy;         // first image row of this thread
         const int tile_x0 = prm.tile_x0[strip];
         const int x_thr = tile_x0 + lane * PC;  // first column of this thread
 
@@ -487,6 +497,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             }
             // only this thread ever reads these values back: no barrier needed
             store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);
+            // a pass after the first continues from the previous pass's result; c' above still used d_0
+            if (prm.init != nullptr && col_in && y < H) {
+                const float4 iv = __ldg(reinterpret_cast<const float4*>(prm.init + (size_t)bc * HW + (size_t)y * W + x_thr));
+                d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
+            }
         }
         __syncthreads();  // every warp is done with the staging buffer
 
@@ -498,17 +513,20 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 issue_stage(next);
             }
             // its blur / sparse rows: pull the lines into L2 (one lane per 128-byte line of the row segment)
-            const int strip_n = next % prm.n_strips, bc_n = next / prm.n_strips;
+            const int strip_n = next % prm.n_strips, q_n = next / prm.n_strips;
+            const int bc_n = q_n / prm.n_bands, yn0 = prm.band_y0[q_n % prm.n_bands] + thr_dy;
             const int xn = prm.tile_x0[strip_n] + lane * PC;
             if ((lane * PC) % 32 == 0 && xn < W) {
                 const float* bn = prm.blur + (size_t)bc_n * HW;
+                const float* in = prm.init ? prm.init + (size_t)bc_n * HW : nullptr;
                 const float* sn = prm.sparse ? prm.sparse + (size_t)(bc_n / prm.C) * HW : nullptr;
 #pragma unroll
                 for (int r = 0; r < PR; ++r) {
-                    const int y = y_thr + r;
+                    const int y = yn0 + r;
                     if (y < H) {
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + xn));
                         if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + xn));
+                        if (in) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (size_t)y * W + xn));
                     }
                 }
             }
@@ -554,11 +572,12 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
         const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
+        const int uy0 = prm.uy0[band], uy1 = prm.uy1[band];   // uy1 <= H
         if (x_thr >= ux0 && x_thr < ux1) {
 #pragma unroll
             for (int r = 0; r < PR; ++r) {
                 const int y = y_thr + r;
-                if (y < H)
+                if (y >= uy0 && y < uy1)
                     __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x_thr), make_float4(d[r][0], d[r][1], d[r][2], d[r][3]));
             }
         }
@@ -597,11 +616,22 @@ const std::vector<KernelCfg>& configs() {
     return v;
 }
 
-struct Plan {
-    int cfg = -1, cs = 0, n_strips = 0;
+// One pass = one launch that advances every image by `iters` steps.
+struct PassPlan {
+    int cfg = -1, cs = 0, iters = 0, max_clusters = 0;
+    int n_strips = 0, n_bands = 0;
     int tile_x0[kMaxStrips], ux0[kMaxStrips], ux1[kMaxStrips];
+    int band_y0[kMaxBands], uy0[kMaxBands], uy1[kMaxBands];
     double cost = 0;
-    int max_clusters = 0;
+};
+// The whole call: n_pass launches; the first n_long of them run `longp` (one step more), the rest `shortp`.
+// Splitting N steps into passes trades one round trip of d through HBM (8 B/px, the kernel is nowhere near HBM-bound)
+// for halos of N/n_pass instead of N columns: at N=48 a 128-column strip would keep only 32 useful columns.
+struct Plan {
+    int n_pass = 0, n_long = 0;
+    PassPlan longp, shortp;
+    double cost = 0;
+    const PassPlan& pass(int i) const { return i < n_long ? longp : shortp; }
 };
 
 std::mutex g_mu;
@@ -650,60 +680,114 @@ int max_active_clusters(int ci, int cs, int dev) {
     return n;
 }
 
-// Strip layout for tile width TW and halo `halo`; returns false if it does not fit kMaxStrips.
-bool layout_strips(int W, int TW, int halo, Plan& p) {
-    p.n_strips = 0;
-    if (TW >= W) {
-        p.tile_x0[0] = 0; p.ux0[0] = 0; p.ux1[0] = W; p.n_strips = 1;
-        return true;
-    }
-    const int halo4 = (halo + 3) & ~3;
-    if (TW - 2 * halo4 < 16) return false;
+// Cover [0, L) with tiles of T positions whose outer `halo` positions (rounded up to `align`) go stale during a pass:
+// tile i starts at t0[i] (a multiple of `align`) and contributes the useful range [u0[i], u1[i]).  Tiles that touch the
+// image border lose nothing on that side (zero padding is the reference's own boundary condition).
+bool layout_1d(int L, int T, int halo, int align, int min_useful, int max_n, int& n, int* t0, int* u0, int* u1) {
+    n = 0;
+    if (T >= L) { t0[0] = 0; u0[0] = 0; u1[0] = L; n = 1; return true; }
+    const int h = (halo + align - 1) / align * align;
+    if (T - 2 * h < min_useful) return false;
     int u = 0;
-    while (u < W) {
-        if (p.n_strips == kMaxStrips) return false;
-        const int x0 = (u == 0) ? 0 : u - halo4;
-        int u1 = (x0 + TW >= W) ? W : x0 + TW - halo4;
-        p.tile_x0[p.n_strips] = x0; p.ux0[p.n_strips] = u; p.ux1[p.n_strips] = u1;
-        ++p.n_strips;
-        u = u1;
+    while (u < L) {
+        if (n == max_n) return false;
+        const int x0 = (u == 0) ? 0 : u - h;
+        const int e = (x0 + T >= L) ? L : x0 + T - h;
+        t0[n] = x0; u0[n] = u; u1[n] = e;
+        ++n;
+        u = e;
     }
     return true;
 }
 
-// Picks (configuration, cluster size, strips) minimising waves x per-task work.  `dev` < 0: no device
-// query (planning on a CPU-only box for describe_plan): assume the B200 occupancy table measured by tools/probe.
-bool make_plan(int B, int C, int H, int W, int iters, int dev, Plan& best, char* why, int why_len) {
-    if (W % 4 != 0) { snprintf(why, why_len, "W=%d is not a multiple of 4 (TMA row pitch / vector stores)", W); return false; }
+// Best (configuration, cluster size, strips, bands) for one pass of `iters` steps: minimises SM time per image.
+// Deliberately independent of B and C, so the same image gets the same tiling (hence bit-identical results) whatever
+// batch it is part of.  `dev` < 0: no device query (planning on a CPU-only box): assume the B200 occupancy table
+// measured by tools/probe.
+bool plan_pass(int H, int W, int iters, int dev, int forced, PassPlan& best) {
     static const int kProbe256[17] = {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7};
+    const char* fcs = getenv("CSPN_B200_FORCE_CS");   // developer hook for tuning runs (with CSPN_B200_FORCE_PASSES)
+    const int forced_cs = fcs ? atoi(fcs) : 0;
     best.cfg = -1;
     const auto& cf = configs();
-    // developer hook for tuning runs: CSPN_B200_FORCE_CFG=<index into configs()>
-    const char* force = getenv("CSPN_B200_FORCE_CFG");
-    const int forced = force ? atoi(force) : -1;
+    const int n_sms = dev >= 0 ? sm_count(dev) : 148;
     for (int ci = 0; ci < (int)cf.size(); ++ci) {
         if (forced >= 0 && ci != forced) continue;
         const KernelCfg& k = cf[ci];
-        const int cs = (H + k.RB() - 1) / k.RB();
-        if (cs > 16) continue;
-        Plan p;
-        if (!layout_strips(W, k.TW(), iters, p)) continue;
-        const int mac = dev >= 0 ? max_active_clusters(ci, cs, dev) : kProbe256[cs];
-        if (mac <= 0) continue;
-        // Steady-state cost per image: strips x per-task work / co-resident clusters.  Deliberately independent of
-        // B and C, so the same image gets the same tiling (hence bit-identical results) whatever batch it is part of.
-        // (when a small configuration fits two CTAs per SM, those CTAs share the SM's FMA pipe: count SMs, not CTAs)
-        const int n_sms = dev >= 0 ? sm_count(dev) : 148;
-        const int ctas_per_sm = (mac * cs + n_sms - 1) / n_sms;
-        p.cost = (double)p.n_strips * k.RB() * k.TW() * (8.0 * iters + 60.0) * ctas_per_sm / mac;
-        p.cfg = ci; p.cs = cs; p.max_clusters = mac;
-        if (best.cfg < 0 || p.cost < best.cost) best = p;
+        PassPlan p;
+        // columns: 4-aligned strip origins (TMA / float4), at least 16 useful columns per strip
+        if (!layout_1d(W, k.TW(), iters, 4, 16, kMaxStrips, p.n_strips, p.tile_x0, p.ux0, p.ux1)) continue;
+        const int cs_full = (H + k.RB() - 1) / k.RB();   // cluster height that needs no row halo
+        for (int cs = 1; cs <= 16 && cs <= cs_full; ++cs) {
+            if (forced_cs > 0 && cs != forced_cs) continue;
+            // rows: one band when the cluster spans the image, else overlapping bands (images taller than 16 CTAs,
+            // or a cluster size that fills the GPCs better)
+            if (!layout_1d(H, cs * k.RB(), iters, 1, 8, kMaxBands, p.n_bands, p.band_y0, p.uy0, p.uy1)) continue;
+            const int mac = dev >= 0 ? max_active_clusters(ci, cs, dev) : kProbe256[cs];
+            if (mac <= 0) continue;
+            // tasks x per-task work / co-resident clusters.  Per-task work: 8 FMA per pixel and step plus a fixed part
+            // (load, normalisation, store) worth ~15 steps (fit of the cfg3 sweep, profiles/r01_all_configs_timing.txt).
+            // When a small configuration fits two CTAs per SM they share the SM's FMA pipe: count SMs, not CTAs.
+            const int ctas_per_sm = (mac * cs + n_sms - 1) / n_sms;
+            p.cost = (double)p.n_strips * p.n_bands * k.RB() * k.TW() * (8.0 * iters + 120.0) * ctas_per_sm / mac;
+            // row bands re-load their halo rows and multiply the task count; measured 7 % slower than this model says
+            // on cfg3 at N=4 (profiles/r01_plan_sweep.txt), so a banded plan has to win by a margin
+            if (p.n_bands > 1) p.cost *= 1.15;
+            p.cfg = ci; p.cs = cs; p.max_clusters = mac; p.iters = iters;
+            if (best.cfg < 0 || p.cost < best.cost) best = p;
+        }
     }
-    if (best.cfg < 0) {
-        snprintf(why, why_len, "no cluster configuration covers H=%d W=%d iters=%d (H too tall for 16 bands or halo too wide)", H, W, iters);
+    return best.cfg >= 0;
+}
+
+struct PlanKey { int H, W, iters, dev, forced; };
+std::vector<std::pair<PlanKey, Plan>> g_plan_cache;   // guarded by g_mu; a handful of shapes per process
+
+// Picks the number of passes and each pass's tiling.  Caller holds g_mu.
+bool make_plan(int H, int W, int iters, int dev, Plan& out, char* why, int why_len) {
+    if (W % 4 != 0) { snprintf(why, why_len, "W=%d is not a multiple of 4 (TMA row pitch / vector stores)", W); return false; }
+    // developer hook for tuning runs: CSPN_B200_FORCE_CFG=<index into configs()>, CSPN_B200_FORCE_PASSES=<n>
+    const char* force = getenv("CSPN_B200_FORCE_CFG");
+    const int forced = force ? atoi(force) : -1;
+    const char* fpass = getenv("CSPN_B200_FORCE_PASSES");
+    const bool no_cache = (fpass && atoi(fpass) > 0) || getenv("CSPN_B200_FORCE_CS") != nullptr;
+    const int forced_passes = fpass ? atoi(fpass) : 0;
+    for (auto& e : g_plan_cache)
+        if (e.first.H == H && e.first.W == W && e.first.iters == iters && e.first.dev == dev && e.first.forced == forced &&
+            !no_cache) { out = e.second; return true; }
+    Plan best;
+    best.n_pass = 0;
+    const int max_pass = iters < kMaxPasses ? iters : kMaxPasses;
+    for (int P = 1; P <= max_pass; ++P) {
+        if (forced_passes > 0 && P != forced_passes) continue;
+        Plan c;
+        c.n_pass = P;
+        c.n_long = iters % P;
+        const int a = iters / P;
+        if (!plan_pass(H, W, a, dev, forced, c.shortp)) continue;
+        if (c.n_long > 0 && !plan_pass(H, W, a + 1, dev, forced, c.longp)) continue;
+        c.cost = (P - c.n_long) * c.shortp.cost + (c.n_long > 0 ? c.n_long * c.longp.cost : 0.0);
+        if (best.n_pass == 0 || c.cost < best.cost) best = c;
+        // more passes only pay while the halo shrinks faster than the fixed per-task part grows
+        if (best.n_pass > 0 && P >= 2 * best.n_pass + 2) break;
+    }
+    if (best.n_pass == 0) {
+        snprintf(why, why_len, "no cluster configuration covers H=%d W=%d iters=%d", H, W, iters);
         return false;
     }
+    if (!no_cache) {
+        if (g_plan_cache.size() >= 64) g_plan_cache.erase(g_plan_cache.begin());
+        g_plan_cache.push_back({PlanKey{H, W, iters, dev, forced}, best});
+    }
+    out = best;
     return true;
+}
+
+int current_device_or_none() {
+    int ndev = 0, dev = -1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return -1; }
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -734,91 +818,133 @@ bool cluster2d_supported(const Problem2D& p, char* why, int why_len) {
         return false;
     }
     if ((long)p.B * p.gch > 2147483647L) { snprintf(why, why_len, "B*gch too large"); return false; }
-    int dev = -1;
-    if (p.blur) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; } }
+    const int dev = current_device_or_none();
     std::lock_guard<std::mutex> lock(g_mu);
     Plan plan;
-    return make_plan(p.B, p.C, p.H, p.W, p.iters, dev, plan, why, why_len);
+    if (!make_plan(p.H, p.W, p.iters, dev, plan, why, why_len)) return false;
+    for (int i = 0; i < 2; ++i) {
+        const PassPlan& pp = i ? plan.shortp : plan.longp;
+        if (pp.cfg >= 0 && (long)p.B * p.C * pp.n_strips * pp.n_bands > 2147483647L) {
+            snprintf(why, why_len, "too many tasks");
+            return false;
+        }
+    }
+    return true;
 }
 
-int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len) {
+// Passes after the first read the previous pass's result: one extra d-sized buffer (passes alternate between it and
+// `out`, ending in `out`).
+size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters) {
+    if (iters <= 0) return 0;
+    const int dev = current_device_or_none();
     std::lock_guard<std::mutex> lock(g_mu);
     Plan plan;
     char why[200] = "";
-    int dev = -1, ndev = 0;
-    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) cudaGetDevice(&dev); else cudaGetLastError();
-    if (!make_plan(B, C, H, W, iters, dev, plan, why, sizeof(why))) return snprintf(buf, len, "cluster: unsupported (%s)", why);
-    const KernelCfg& k = configs()[plan.cfg];
-    long useful = 0;
-    for (int i = 0; i < plan.n_strips; ++i) useful += plan.ux1[i] - plan.ux0[i];
-    return snprintf(buf, len,
-                    "cluster: patch %dx%d px/thread, %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
-                    "%d strip(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
-                    k.PR, k.PC, k.NW, k.RB(), k.TW(), plan.cs, plan.cs * k.RB(), plan.n_strips, (long)B * C * plan.n_strips,
-                    plan.max_clusters, (double)useful * H / ((double)plan.n_strips * k.TW() * plan.cs * k.RB()), k.smem);
+    if (!make_plan(H, W, iters, dev, plan, why, sizeof(why))) return 0;
+    return plan.n_pass > 1 ? (size_t)B * C * H * W * sizeof(float) : 0;
 }
 
-int cluster2d_forward(const Problem2D& p, cudaStream_t stream, int* launches) {
+int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len) {
+    const int dev = current_device_or_none();
+    std::lock_guard<std::mutex> lock(g_mu);
+    Plan plan;
+    char why[200] = "";
+    if (!make_plan(H, W, iters, dev, plan, why, sizeof(why))) return snprintf(buf, len, "cluster: unsupported (%s)", why);
+    const PassPlan& pp = plan.shortp;
+    const KernelCfg& k = configs()[pp.cfg];
+    long useful_x = 0, useful_y = 0;
+    for (int i = 0; i < pp.n_strips; ++i) useful_x += pp.ux1[i] - pp.ux0[i];
+    for (int i = 0; i < pp.n_bands; ++i) useful_y += pp.uy1[i] - pp.uy0[i];
+    char passes[96] = "";
+    if (plan.n_pass > 1)
+        snprintf(passes, sizeof(passes), "%d passes (%d x %d + %d x %d steps), ", plan.n_pass, plan.n_long, pp.iters + 1,
+                 plan.n_pass - plan.n_long, pp.iters);
+    return snprintf(buf, len,
+                    "cluster: %spatch %dx%d px/thread, %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
+                    "%d strip(s) x %d band(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
+                    passes, k.PR, k.PC, k.NW, k.RB(), k.TW(), pp.cs, pp.cs * k.RB(), pp.n_strips, pp.n_bands,
+                    (long)B * C * pp.n_strips * pp.n_bands, pp.max_clusters,
+                    (double)useful_x * useful_y / ((double)pp.n_strips * k.TW() * pp.n_bands * pp.cs * k.RB()), k.smem);
+}
+
+int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {
     int dev = 0;
     CSPN_CUDA_TRY(cudaGetDevice(&dev));
     Plan plan;
     {
         std::lock_guard<std::mutex> lock(g_mu);
         char why[200] = "";
-        if (!make_plan(p.B, p.C, p.H, p.W, p.iters, dev, plan, why, sizeof(why))) {
+        if (!make_plan(p.H, p.W, p.iters, dev, plan, why, sizeof(why))) {
             set_error("cluster kernel unsupported: %s", why);
             return CSPN_ERR_UNSUPPORTED;
         }
         int rc = get_encode();
         if (rc != CSPN_OK) return rc;
     }
-    const KernelCfg& k = configs()[plan.cfg];
+    const size_t d_bytes = (size_t)p.B * p.C * p.H * p.W * sizeof(float);
+    if (plan.n_pass > 1 && (!ws || ws_bytes < d_bytes)) {
+        set_error("cluster path splits %d steps into %d passes and needs %zu workspace bytes, got %zu", p.iters, plan.n_pass,
+                  d_bytes, ws ? ws_bytes : (size_t)0);
+        return CSPN_ERR_WORKSPACE;
+    }
 
-    // guidance as a 3D tensor (W, H, B*gch); one box = (TW, RB, 1) floats of one channel plane
-    CUtensorMap tm;
     const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
     const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H, p.B * p.gch,
-                  k.TW(), k.RB());
-        return CSPN_ERR_CUDA;
-    }
+    const float* prev = nullptr;   // result of the previous pass
+    for (int ip = 0; ip < plan.n_pass; ++ip) {
+        const PassPlan& pp = plan.pass(ip);
+        const KernelCfg& k = configs()[pp.cfg];
+        // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane
+        CUtensorMap tm;
+        const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
+        CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H,
+                      p.B * p.gch, k.TW(), k.RB());
+            return CSPN_ERR_CUDA;
+        }
+        // passes alternate between the workspace and `out` such that the last one lands in `out`
+        float* dst = ((plan.n_pass - 1 - ip) & 1) ? static_cast<float*>(ws) : p.out;
 
-    ClusterParams prm;
-    prm.blur = p.blur; prm.sparse = p.sparse; prm.out = p.out;
-    prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = p.iters; prm.norm_abs = p.norm_abs;
-    prm.n_strips = plan.n_strips;
-    prm.n_tasks = (int)((long)p.B * p.C * plan.n_strips);
-    for (int i = 0; i < kMaxStrips; ++i) {
-        prm.tile_x0[i] = i < plan.n_strips ? plan.tile_x0[i] : 0;
-        prm.ux0[i] = i < plan.n_strips ? plan.ux0[i] : 0;
-        prm.ux1[i] = i < plan.n_strips ? plan.ux1[i] : 0;
-    }
-    const long tasks = (long)p.B * p.C * plan.n_strips;
-    if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
-    // persistent clusters: as many as fit on the device at once, each looping over tasks
-    const long n_clusters = tasks < plan.max_clusters ? tasks : plan.max_clusters;
+        ClusterParams prm;
+        prm.blur = p.blur; prm.init = prev; prm.sparse = p.sparse; prm.out = dst;
+        prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = pp.iters; prm.norm_abs = p.norm_abs;
+        prm.n_strips = pp.n_strips;
+        prm.n_bands = pp.n_bands;
+        const long tasks = (long)p.B * p.C * pp.n_strips * pp.n_bands;
+        if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
+        prm.n_tasks = (int)tasks;
+        for (int i = 0; i < kMaxStrips; ++i) {
+            const bool in = i < pp.n_strips;
+            prm.tile_x0[i] = in ? pp.tile_x0[i] : 0; prm.ux0[i] = in ? pp.ux0[i] : 0; prm.ux1[i] = in ? pp.ux1[i] : 0;
+        }
+        for (int i = 0; i < kMaxBands; ++i) {
+            const bool in = i < pp.n_bands;
+            prm.band_y0[i] = in ? pp.band_y0[i] : 0; prm.uy0[i] = in ? pp.uy0[i] : 0; prm.uy1[i] = in ? pp.uy1[i] : 0;
+        }
+        // persistent clusters: as many as fit on the device at once, each looping over tasks
+        const long n_clusters = tasks < pp.max_clusters ? tasks : pp.max_clusters;
 
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_clusters * plan.cs));
-    cfg.blockDim = dim3(32 * k.NW);
-    cfg.dynamicSmemBytes = k.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = plan.cs;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    void* args[2] = {(void*)&tm, (void*)&prm};
-    CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn[p.norm_abs ? 1 : 0], args));
-    ++*launches;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_clusters * pp.cs));
+        cfg.blockDim = dim3(32 * k.NW);
+        cfg.dynamicSmemBytes = k.smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = pp.cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        void* args[2] = {(void*)&tm, (void*)&prm};
+        CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn[p.norm_abs ? 1 : 0], args));
+        ++*launches;
+        prev = dst;
+    }
     return CSPN_OK;
 }
 

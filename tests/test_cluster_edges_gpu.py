@@ -36,10 +36,45 @@ def test_tilings_match_oracle(H, W, n):
     check(1, 1, H, W, n, expect='cluster')
 
 
+@pytest.mark.parametrize('H,W,n', [
+    (700, 64, 4),       # taller than 16 CTAs of 40 rows: overlapping row bands
+    (1000, 256, 30),    # bands x strips, both with halos
+    (650, 128, 3),      # one strip, bands with a 3-row halo
+    (24, 512, 70),      # halo wider than a strip can carry: several passes through HBM
+    (228, 304, 48),     # cfg3's longest run: 3 passes of 16 steps
+    (100, 132, 131),    # odd step count split into passes of unequal length
+    (352, 1216, 49),
+])
+def test_tall_images_and_long_runs_stay_on_the_cluster_path(H, W, n):
+    check(1, 1, H, W, n, expect='cluster')
+    assert _lib.lib().cspn_last_launches() >= 1
+
+
+def test_multi_pass_with_channels_abs_norm_and_no_sparse():
+    check(2, 3, 60, 260, 90, '8sum_abs', gch=9, sparse=None, expect='cluster')
+    assert _lib.lib().cspn_last_launches() > 1
+
+
+def test_multi_pass_through_the_host_entry_point():
+    g, d, s = make_inputs(11, 3, 1, 64, 256, 8, 'signed', 100)
+    ref = c_oracle.cspn2d(g.numpy(), d.numpy(), s.numpy(), 80, '8sum')
+    out = cspn_b200.propagate2d(g, d, s, 80, '8sum')        # CPU tensors -> cspn2d_fwd_f32_host
+    assert not out.is_cuda and onp.parity_ok(out.numpy(), ref, 1e-4)[0]
+
+
+def test_missing_workspace_is_reported_not_ignored():
+    g, d, s = [t.cuda() for t in make_inputs(3, 1, 1, 64, 256)]
+    L = _lib.lib()
+    out = torch.empty_like(d)
+    need = L.cspn2d_workspace_bytes(1, 1, 64, 256, 120, _lib.ALGO_CLUSTER)
+    assert need == d.numel() * 4
+    rc = L.cspn2d_fwd_f32(g.data_ptr(), d.data_ptr(), s.data_ptr(), out.data_ptr(), 1, 1, 64, 256, 8, 120, 0,
+                          _lib.ALGO_CLUSTER, None, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == -2 and b'workspace' in L.cspn_last_error()
+
+
 def test_shapes_the_cluster_kernel_declines_fall_back_to_generic():
-    check(1, 1, 700, 64, 4, expect='generic')       # more than 16 bands of 40 rows
     check(1, 1, 20, 18, 4, expect='generic')        # W % 4 != 0
-    check(1, 1, 24, 512, 70, expect='generic')      # halo wider than a strip can carry
     with pytest.raises(cspn_b200.CspnError):
         check(1, 1, 20, 18, 4, algo=_lib.ALGO_CLUSTER)
 
@@ -57,26 +92,27 @@ def test_misaligned_views_are_handled():
     assert onp.parity_ok(out.cpu().numpy(), ref, 1e-4)[0]
 
 
-def test_cuda_graph_capture_and_replay():
+@pytest.mark.parametrize('n', [24, 48])      # 48: three passes, i.e. three launches inside the graph
+def test_cuda_graph_capture_and_replay(n):
     """No allocation / synchronisation inside the C ABI call: it can be captured in a CUDA graph."""
     g, d, s = [t.cuda() for t in make_inputs(3, 4, 1, 228, 304)]
     L = _lib.lib()
     out = torch.empty_like(d)
-    ws_bytes = L.cspn2d_workspace_bytes(4, 1, 228, 304, 24, _lib.ALGO_AUTO)
+    ws_bytes = L.cspn2d_workspace_bytes(4, 1, 228, 304, n, _lib.ALGO_AUTO)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device='cuda')
     st = torch.cuda.Stream()
     st.wait_stream(torch.cuda.current_stream())
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(st):
         def call():
-            rc = L.cspn2d_fwd_f32(g.data_ptr(), d.data_ptr(), s.data_ptr(), out.data_ptr(), 4, 1, 228, 304, 8, 24, 0,
+            rc = L.cspn2d_fwd_f32(g.data_ptr(), d.data_ptr(), s.data_ptr(), out.data_ptr(), 4, 1, 228, 304, 8, n, 0,
                                   _lib.ALGO_AUTO, ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream)
             assert rc == 0, L.cspn_last_error()
         call()                                       # warm-up outside capture (sets function attributes)
         torch.cuda.current_stream().synchronize()
         with torch.cuda.graph(graph, stream=st):
             call()
-    ref = cspn_b200.propagate2d(g, d, s, 24, '8sum')
+    ref = cspn_b200.propagate2d(g, d, s, n, '8sum')
     d.mul_(0.5)                                      # new input values, same buffers
     graph.replay()
     torch.cuda.synchronize()
