@@ -64,8 +64,9 @@ typedef enum {
 typedef enum {
     CSPN_ALGO_AUTO = 0,    /* cluster kernel when the shape allows, else generic                         */
     CSPN_ALGO_GENERIC = 1, /* prep kernel + one stencil launch per iteration (any shape; needs workspace) */
-    CSPN_ALGO_CLUSTER = 2  /* single launch: TMA-staged tiles, register-resident state for all iterations,
-                              DSMEM halo exchange inside a thread-block cluster                          */
+    CSPN_ALGO_CLUSTER = 2  /* TMA-staged tiles, register-resident state for all iterations of a launch, DSMEM halo
+                              exchange inside a thread-block cluster.  One launch for prop_time <~ 24-32; longer
+                              runs are split into passes and then need a workspace of B*C*H*W floats          */
 } cspn_algo;
 
 /* ---- 2D: replaces Affinity_Propagate.forward (cspn.py:42-83) --------------------------------
