@@ -5,7 +5,11 @@
 // (PARITY UNPINNED, see oracle/cspn_numpy.py).  Per-voxel state is 26 weights + kappa + value
 // (112 B of input per voxel); with N = 12 and a 3D halo no on-chip temporal blocking fits an
 // SM's 64K registers, so this path streams the normalised weights once per iteration from
-// L2/HBM, one volume at a time (the 27*D*H*W workspace of one volume is reused for the batch).
+// L2/HBM.  Volumes are processed in groups (grid z carries the volume index): one step launch covers the whole
+// group, because a single volume's step lasts only ~46 us and launch gaps + ramp/tail cost 15 % at that size;
+// the group is capped so that the 27*D*H*W-float workspace per volume stays below kMaxWorkspace3d.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cspn {
@@ -17,10 +21,12 @@ __global__ void __launch_bounds__(256)
 prep3d_kernel(const float* __restrict__ g, float* __restrict__ wk, int D, int H, int W, int mode) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = blockIdx.z;
+    const int z = blockIdx.z % D, vol = blockIdx.z / D;
     if (x >= W || y >= H) return;
     const size_t HW = (size_t)H * W, V = (size_t)D * HW;
     const size_t p = (size_t)z * HW + (size_t)y * W + x;
+    g += (size_t)vol * 26 * V;
+    wk += (size_t)vol * 27 * V;
     float a[26], S = 0.f;
 #pragma unroll
     for (int k = 0; k < 26; ++k) {
@@ -50,13 +56,14 @@ prep3d_kernel(const float* __restrict__ g, float* __restrict__ wk, int D, int H,
 
 __global__ void __launch_bounds__(256)
 step3d_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const float* __restrict__ cur,
-              float* __restrict__ dst, int D, int H, int W) {
+              float* __restrict__ dst, int C, int D, int H, int W) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = blockIdx.z % D, c = blockIdx.z / D;
+    const int z = blockIdx.z % D, c = blockIdx.z / D;   // c = volume * C + channel
     if (x >= W || y >= H) return;
     const size_t HW = (size_t)H * W, V = (size_t)D * HW;
     const size_t p = (size_t)z * HW + (size_t)y * W + x;
+    wk += (size_t)(c / C) * 27 * V;
     const float* cc = cur + (size_t)c * V;
     float acc = __ldg(wk + 26 * V + p) * __ldg(d0 + (size_t)c * V + p);
 #pragma unroll
@@ -74,13 +81,14 @@ step3d_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const 
 // current volume are read as one aligned float4 plus two edge scalars each (L1/L2 hits).
 __global__ void __launch_bounds__(128)
 step3d_vec4_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const float* __restrict__ cur,
-                   float* __restrict__ dst, int D, int H, int W) {
+                   float* __restrict__ dst, int C, int D, int H, int W) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = blockIdx.z % D, c = blockIdx.z / D;
+    const int z = blockIdx.z % D, c = blockIdx.z / D;   // c = volume * C + channel
     if (x >= W || y >= H) return;
     const size_t HW = (size_t)H * W, V = (size_t)D * HW;
     const size_t p = (size_t)z * HW + (size_t)y * W + x;
+    wk += (size_t)(c / C) * 27 * V;
     const float* cc = cur + (size_t)c * V;
     // rows[dz+1][dy+1][0..5] = cur(z+dz, y+dy, x-1 .. x+4), zero outside the volume
     float rows[3][3][6];
@@ -119,10 +127,25 @@ step3d_vec4_kernel(const float* __restrict__ wk, const float* __restrict__ d0, c
 
 }  // namespace
 
+// Volumes per launch group: as many as keep the group's workspace under kMaxWorkspace3d (and gridDim.z legal).
+constexpr size_t kMaxWorkspace3d = (size_t)4 << 30;
+static int group3d(int B, int C, int D, int H, int W, int iters) {
+    const size_t V = (size_t)D * H * W;
+    const size_t per_vol = sizeof(float) * (27 * V + (iters > 1 ? (size_t)C * V : 0));
+    size_t cap = kMaxWorkspace3d;
+    if (const char* e = getenv("CSPN_B200_MAX_WS3D_KB"))   // developer hook: tests force small / ragged groups
+        if (atof(e) > 0) cap = (size_t)(atof(e) * 1024.0);
+    size_t g = cap / per_vol;
+    const size_t gz = 65535 / ((size_t)D * C);
+    if (g > gz) g = gz;
+    if (g > (size_t)B) g = B;
+    return g < 1 ? 1 : (int)g;
+}
+
 size_t generic3d_workspace_bytes(int B, int C, int D, int H, int W, int iters) {
     if (iters <= 0) return 0;
     const size_t V = (size_t)D * H * W;
-    return sizeof(float) * (27 * V + (iters > 1 ? (size_t)C * V : 0));
+    return sizeof(float) * (size_t)group3d(B, C, D, H, W, iters) * (27 * V + (iters > 1 ? (size_t)C * V : 0));
 }
 
 int generic3d_forward(const float* guidance, const float* feat, float* out, int B, int C, int D, int H, int W,
@@ -142,24 +165,26 @@ int generic3d_forward(const float* guidance, const float* feat, float* out, int 
         set_error("3D path: D*C=%zu exceeds gridDim.z", (size_t)D * C);
         return CSPN_ERR_UNSUPPORTED;
     }
-    float* wk = static_cast<float*>(ws);
-    float* tmp = wk + 27 * V;
+    const int G = group3d(B, C, D, H, W, iters);
+    float* wk = static_cast<float*>(ws);          // [G][27][V]
+    float* tmp = wk + (size_t)G * 27 * V;         // [G][C][V]
     const dim3 block(32, 8);
     const dim3 g2((W + 31) / 32, (H + 7) / 8);
-    for (int b = 0; b < B; ++b) {
-        const float* d0 = feat + (size_t)b * C * V;
-        float* o = out + (size_t)b * C * V;
-        prep3d_kernel<<<dim3(g2.x, g2.y, D), block, 0, stream>>>(guidance + (size_t)b * 26 * V, wk, D, H, W, mode);
+    const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out) |
+                                          reinterpret_cast<uintptr_t>(ws)) % 16 == 0);
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int n = (B - b0 < G) ? B - b0 : G;  // volumes in this group
+        const float* d0 = feat + (size_t)b0 * C * V;
+        float* o = out + (size_t)b0 * C * V;
+        prep3d_kernel<<<dim3(g2.x, g2.y, D * n), block, 0, stream>>>(guidance + (size_t)b0 * 26 * V, wk, D, H, W, mode);
         ++*launches;
         const float* cur = d0;
         float* dst = (iters & 1) ? o : tmp;
-        const bool vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out) |
-                                              reinterpret_cast<uintptr_t>(ws)) % 16 == 0);
         for (int it = 0; it < iters; ++it) {
             if (vec4)
-                step3d_vec4_kernel<<<dim3((W / 4 + 31) / 32, (H + 3) / 4, D * C), dim3(32, 4), 0, stream>>>(wk, d0, cur, dst, D, H, W);
+                step3d_vec4_kernel<<<dim3((W / 4 + 31) / 32, (H + 3) / 4, D * C * n), dim3(32, 4), 0, stream>>>(wk, d0, cur, dst, C, D, H, W);
             else
-                step3d_kernel<<<dim3(g2.x, g2.y, D * C), block, 0, stream>>>(wk, d0, cur, dst, D, H, W);
+                step3d_kernel<<<dim3(g2.x, g2.y, D * C * n), block, 0, stream>>>(wk, d0, cur, dst, C, D, H, W);
             ++*launches;
             cur = dst;
             dst = (dst == o) ? tmp : o;
@@ -301,7 +326,7 @@ int bwd3d(const float* guidance, const float* feat, const float* grad_out, float
         ++*launches;
         for (int t = 0; t + 1 < iters; ++t) {
             step3d_kernel<<<dim3(g2.x, g2.y, D * C), block, 0, stream>>>(wk, d0, t == 0 ? d0 : Dt + (size_t)(t - 1) * n,
-                                                                         Dt + (size_t)t * n, D, H, W);
+                                                                         Dt + (size_t)t * n, C, D, H, W);
             ++*launches;
         }
         const float* lam_in = grad_out + (size_t)b * n;

@@ -41,7 +41,7 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     assert L.cspn2d_fwd_f32(p, p, None, p, 1, 1, 4, 4, 8, 1, 5, 0, None, 0, None) == -1       # unknown norm
     assert L.cspn2d_fwd_f32(p, p, None, p, 1, 1, 4, 4, 8, -1, 0, 0, None, 0, None) == -1      # negative iters
     assert L.cspn2d_workspace_bytes(2, 1, 10, 15, 3, _lib.ALGO_GENERIC) == 4 * (2 * 9 * 150 + 2 * 150)
-    assert L.cspn3d_workspace_bytes(2, 1, 3, 4, 5, 2) == 4 * (27 * 60 + 60)
+    assert L.cspn3d_workspace_bytes(2, 1, 3, 4, 5, 2) == 2 * 4 * (27 * 60 + 60)   # both volumes form one launch group
     assert isinstance(cspn_b200.describe_plan(32, 1, 352, 1216, 24), str)
 
 

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 import cspn_b200
+from cspn_b200 import _lib
 from cspn_b200.synth import make_inputs_3d
 from oracle import c_oracle, cspn_numpy as onp
 
@@ -39,6 +40,20 @@ def test_3d_full_size_properties():
                           const[:, :, 12:-12, 12:-12, 12:-12], rtol=1e-5)
     ref = c_oracle.cspn3d(g[:1].cpu().numpy(), f[:1].cpu().numpy(), 12, '26sum_abs')
     ok, ratio, normwise = onp.parity_ok(out[:1].cpu().numpy(), ref, 1e-4)
+    assert ok, (ratio, normwise)
+
+
+@pytest.mark.parametrize('cap_kb,launches', [(None, 1 + 4), (300, 2 * (1 + 4)), (100, 3 * (1 + 4))])
+def test_3d_volume_groups_including_a_ragged_last_group(cap_kb, launches, monkeypatch):
+    """One launch covers a group of volumes; the workspace cap decides the group size (3 volumes: 3, 2+1, 1+1+1)."""
+    if cap_kb:
+        monkeypatch.setenv('CSPN_B200_MAX_WS3D_KB', str(cap_kb))     # one volume needs 29 * 6*10*16 * 4 B = 111 KB
+    g, f = make_inputs_3d(4, 3, 2, 6, 10, 16)
+    ref = c_oracle.cspn3d(g.numpy(), f.numpy(), 4, '26sum_abs')
+    out = cspn_b200.propagate3d(g.cuda(), f.cuda(), 4, '26sum_abs')
+    torch.cuda.synchronize()
+    assert _lib.lib().cspn_last_launches() == launches
+    ok, ratio, normwise = onp.parity_ok(out.cpu().numpy(), ref, 1e-4)
     assert ok, (ratio, normwise)
 
 
