@@ -333,7 +333,9 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
 }
 
-template <int PR, int PC, int NW, bool ABS>
+// GENERAL = false compiles out row bands and the continuation input of multi-pass plans: the common single-pass,
+// single-band launch (every BASELINE 2D config) pays nothing for them.
+template <int PR, int PC, int NW, bool ABS, bool GENERAL>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
     using K = Cfg<PR, PC, NW>;
@@ -381,13 +383,13 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     auto issue_stage = [&](int t) {
         const int strip_t = t % prm.n_strips;
         const int q_t = t / prm.n_strips;
-        const int band_t = q_t % prm.n_bands;
-        const int b_t = (q_t / prm.n_bands) / prm.C;
+        const int band_t = GENERAL ? q_t % prm.n_bands : 0;
+        const int b_t = (GENERAL ? q_t / prm.n_bands : q_t) / prm.C;
         mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             tma_load_3d(smem_u32(stage) + (uint32_t)(k * K::kPlaneBytes), &tm_guidance, prm.tile_x0[strip_t] - 4,
-                        prm.band_y0[band_t] + cta_dy + off2_dy(k), b_t * prm.gch + k, bar_tma);
+                        (GENERAL ? prm.band_y0[band_t] : 0) + cta_dy + off2_dy(k), b_t * prm.gch + k, bar_tma);
     };
 
     if (tid == 0) {
@@ -414,10 +416,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
         const int strip = task % prm.n_strips;
-        const int band = (task / prm.n_strips) % prm.n_bands;
-        const int bc = (task / prm.n_strips) / prm.n_bands;  // b*C + c
+        const int band = GENERAL ? (task / prm.n_strips) % prm.n_bands : 0;
+        const int bc = GENERAL ? (task / prm.n_strips) / prm.n_bands : task / prm.n_strips;  // b*C + c
         const int b = bc / prm.C;
-        const int y_thr = prm.band_y0[band] + thr_dy;         // first image row of this thread
+        const int y_thr = (GENERAL ? prm.band_y0[band] : 0) + thr_dy;   // first image row of this thread
+        const float* init = GENERAL ? prm.init : nullptr;
         const int tile_x0 = prm.tile_x0[strip];
         const int x_thr = tile_x0 + lane * PC;  // first column of this thread
 
@@ -498,8 +501,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             // only this thread ever reads these values back: no barrier needed
             store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);
             // a pass after the first continues from the previous pass's result; c' above still used d_0
-            if (prm.init != nullptr && col_in && y < H) {
-                const float4 iv = __ldg(reinterpret_cast<const float4*>(prm.init + (size_t)bc * HW + (size_t)y * W + x_thr));
+            if (GENERAL && init != nullptr && col_in && y < H) {
+                const float4 iv = __ldg(reinterpret_cast<const float4*>(init + (size_t)bc * HW + (size_t)y * W + x_thr));
                 d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
             }
         }
@@ -514,11 +517,12 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             }
             // its blur / sparse rows: pull the lines into L2 (one lane per 128-byte line of the row segment)
             const int strip_n = next % prm.n_strips, q_n = next / prm.n_strips;
-            const int bc_n = q_n / prm.n_bands, yn0 = prm.band_y0[q_n % prm.n_bands] + thr_dy;
+            const int bc_n = GENERAL ? q_n / prm.n_bands : q_n;
+            const int yn0 = (GENERAL ? prm.band_y0[q_n % prm.n_bands] : 0) + thr_dy;
             const int xn = prm.tile_x0[strip_n] + lane * PC;
             if ((lane * PC) % 32 == 0 && xn < W) {
                 const float* bn = prm.blur + (size_t)bc_n * HW;
-                const float* in = prm.init ? prm.init + (size_t)bc_n * HW : nullptr;
+                const float* in = (GENERAL && init) ? init + (size_t)bc_n * HW : nullptr;
                 const float* sn = prm.sparse ? prm.sparse + (size_t)(bc_n / prm.C) * HW : nullptr;
 #pragma unroll
                 for (int r = 0; r < PR; ++r) {
@@ -572,7 +576,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
         const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
-        const int uy0 = prm.uy0[band], uy1 = prm.uy1[band];   // uy1 <= H
+        const int uy0 = GENERAL ? prm.uy0[band] : 0, uy1 = GENERAL ? prm.uy1[band] : H;   // uy1 <= H
         if (x_thr >= ux0 && x_thr < ux1) {
 #pragma unroll
             for (int r = 0; r < PR; ++r) {
@@ -590,7 +594,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
 struct KernelCfg {
     int PR, PC, NW;
-    const void* fn[2];  // [norm_abs]
+    const void* fn[2][2];  // [general][norm_abs]
     size_t smem;
     int RB() const { return PR * NW; }
     int TW() const { return 32 * PC; }
@@ -599,7 +603,8 @@ struct KernelCfg {
 template <int PR, int PC, int NW>
 KernelCfg make_cfg() {
     return KernelCfg{PR, PC, NW,
-                     {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true>},
+                     {{(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, false>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, false>},
+                      {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, true>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true>}},
                      Cfg<PR, PC, NW>::kSmemBytes};
 }
 
@@ -655,9 +660,9 @@ int max_active_clusters(int ci, int cs, int dev) {
         if (e.first.cfg == ci && e.first.cs == cs && e.first.dev == dev) return e.second;
     const KernelCfg& k = configs()[ci];
     if (!g_attr_set[dev & 15][ci]) {
-        for (int ab = 0; ab < 2; ++ab)
-            if (cudaFuncSetAttribute(k.fn[ab], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
-                cudaFuncSetAttribute(k.fn[ab], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        for (int ab = 0; ab < 4; ++ab)
+            if (cudaFuncSetAttribute(k.fn[ab >> 1][ab & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
+                cudaFuncSetAttribute(k.fn[ab >> 1][ab & 1], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                 cudaGetLastError();
                 return 0;
             }
@@ -675,7 +680,7 @@ int max_active_clusters(int ci, int cs, int dev) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k.fn[0], &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, k.fn[1][0], &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
     g_occ_cache.push_back({OccKey{ci, cs, dev}, n});
     return n;
 }
@@ -941,7 +946,8 @@ int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_
         cfg.attrs = at;
         cfg.numAttrs = 1;
         void* args[2] = {(void*)&tm, (void*)&prm};
-        CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn[p.norm_abs ? 1 : 0], args));
+        const bool general = pp.n_bands > 1 || prev != nullptr;
+        CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn[general ? 1 : 0][p.norm_abs ? 1 : 0], args));
         ++*launches;
         prev = dst;
     }
