@@ -193,6 +193,12 @@ int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int algo, char* 
                     generic2d_workspace_bytes(B, C, H, W, iters), why[0] ? "; cluster kernel not used: " : "", why);
 }
 
+int cspn2d_plan_json(int H, int W, int iters, char* buf, int buf_len) {
+    if (!buf || buf_len <= 0) return 0;
+    if (H <= 0 || W <= 0 || iters <= 0) return snprintf(buf, buf_len, "{\"supported\": false, \"why\": \"invalid shape\"}");
+    return cluster2d_plan_json(H, W, iters, buf, buf_len);
+}
+
 }  // extern "C"
 
 // ---- host-buffer pipeline -------------------------------------------------------------------

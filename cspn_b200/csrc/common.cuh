@@ -62,6 +62,7 @@ bool cluster2d_supported(const Problem2D& p, char* why, int why_len);
 size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters);
 int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
 int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len);
+int cluster2d_plan_json(int H, int W, int iters, char* buf, int len);
 
 void launch_prep2d(const float* guidance, const float* sparse, float* wk, int B, int H, int W, int gch, int norm_abs,
                    cudaStream_t stream);

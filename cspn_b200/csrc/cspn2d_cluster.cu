@@ -39,9 +39,9 @@ namespace cspn {
 
 namespace {
 
-constexpr int kMaxStrips = 40;
+constexpr int kMaxStrips = 128;
 constexpr int kMaxBands = 64;
-constexpr int kMaxPasses = 64;
+constexpr int kMaxPasses = 1024;
 
 struct ClusterParams {
     const float* blur;    // [B*C][H][W]  d_0: the constant term always comes from here (cspn.py:58,76,81)
@@ -870,6 +870,31 @@ int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len
                     passes, k.PR, k.PC, k.NW, k.RB(), k.TW(), pp.cs, pp.cs * k.RB(), pp.n_strips, pp.n_bands,
                     (long)B * C * pp.n_strips * pp.n_bands, pp.max_clusters,
                     (double)useful_x * useful_y / ((double)pp.n_strips * k.TW() * pp.n_bands * pp.cs * k.RB()), k.smem);
+}
+
+// Machine-readable plan (tests/test_plan_cpu.py replays it on the CPU oracle): every pass with its tile geometry.
+int cluster2d_plan_json(int H, int W, int iters, char* buf, int len) {
+    const int dev = current_device_or_none();
+    std::lock_guard<std::mutex> lock(g_mu);
+    Plan plan;
+    char why[200] = "";
+    if (!make_plan(H, W, iters, dev, plan, why, sizeof(why))) return snprintf(buf, len, "{\"supported\": false, \"why\": \"%s\"}", why);
+    int n = snprintf(buf, len, "{\"supported\": true, \"passes\": [");
+    for (int part = 0; part < 2; ++part) {
+        const int count = part == 0 ? plan.n_long : plan.n_pass - plan.n_long;
+        if (count == 0) continue;
+        const PassPlan& pp = part == 0 ? plan.longp : plan.shortp;
+        const KernelCfg& k = configs()[pp.cfg];
+        auto put = [&](const char* fmt, auto... a) { if (n < len) n += snprintf(buf + n, len - n, fmt, a...); };
+        put("%s{\"count\": %d, \"iters\": %d, \"PR\": %d, \"NW\": %d, \"RB\": %d, \"TW\": %d, \"cs\": %d, \"max_clusters\": %d, \"strips\": [",
+            (part == 1 && plan.n_long > 0) ? ", " : "", count, pp.iters, k.PR, k.NW, k.RB(), k.TW(), pp.cs, pp.max_clusters);
+        for (int i = 0; i < pp.n_strips; ++i) put("%s[%d, %d, %d]", i ? ", " : "", pp.tile_x0[i], pp.ux0[i], pp.ux1[i]);
+        put("], \"bands\": [");
+        for (int i = 0; i < pp.n_bands; ++i) put("%s[%d, %d, %d]", i ? ", " : "", pp.band_y0[i], pp.uy0[i], pp.uy1[i]);
+        put("]}");
+    }
+    if (n < len) n += snprintf(buf + n, len - n, "]}");
+    return n;
 }
 
 int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {

@@ -128,6 +128,10 @@ CSPN_API int cspn_last_algo(void);            /* cspn_algo actually used by this
 CSPN_API int cspn_last_launches(void);        /* kernels this thread's last call launched */
 /* Human-readable plan for a 2D shape (tile geometry, cluster size, strips); returns bytes written. */
 CSPN_API int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int algo, char* buf, int buf_len);
+/* The cluster path's plan as JSON: passes (count, steps, tile geometry) with their strips [tile_x0, ux0, ux1] and
+ * row bands [band_y0, uy0, uy1]; {"supported": false, ...} when the shape goes to the generic path.  Returns the
+ * bytes needed (output is truncated to buf_len). */
+CSPN_API int cspn2d_plan_json(int H, int W, int iters, char* buf, int buf_len);
 
 #ifdef __cplusplus
 }
