@@ -75,6 +75,8 @@ def propagate2d(guidance, blur_depth, sparse_depth=None, prop_time=24, norm_type
     if out is None:
         out = torch.empty_like(d)
     _check_out(out, d)
+    if algo == ALGO_AUTO and any(t is not None and t.data_ptr() % 16 for t in (g, d, s, out)):
+        algo = ALGO_GENERIC   # views at odd storage offsets: the cluster kernel's TMA / float4 accesses need 16-byte bases
     with torch.cuda.device(d.device):
         ws_bytes = L.cspn2d_workspace_bytes(B, C, H, W, int(prop_time), algo)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d.device) if ws_bytes else None

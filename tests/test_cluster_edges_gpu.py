@@ -92,6 +92,20 @@ def test_misaligned_views_are_handled():
     assert onp.parity_ok(out.cpu().numpy(), ref, 1e-4)[0]
 
 
+def test_tensors_at_odd_storage_offsets_take_the_generic_path():
+    """A contiguous view whose base is only 4-byte aligned cannot feed TMA / float4 accesses: AUTO must not fail."""
+    g, d, s = make_inputs(7, 1, 1, 40, 128)
+    ref = c_oracle.cspn2d(g.numpy(), d.numpy(), s.numpy(), 6, '8sum')
+    flat = torch.empty(d.numel() + 1, device='cuda')
+    dv = flat[1:].view(d.shape)
+    dv.copy_(d)
+    assert dv.data_ptr() % 16 == 4 and dv.is_contiguous()
+    out = cspn_b200.propagate2d(g.cuda(), dv, s.cuda(), 6, '8sum')
+    torch.cuda.synchronize()
+    assert _lib.ALGO_NAMES[_lib.lib().cspn_last_algo()] == 'generic'
+    assert onp.parity_ok(out.cpu().numpy(), ref, 1e-4)[0]
+
+
 @pytest.mark.parametrize('n', [24, 48])      # 48: three passes, i.e. three launches inside the graph
 def test_cuda_graph_capture_and_replay(n):
     """No allocation / synchronisation inside the C ABI call: it can be captured in a CUDA graph."""
