@@ -48,6 +48,8 @@ struct ClusterParams {
     const float* init;    // [B*C][H][W]  d at the start of this pass (null: d_0) -- passes after the first
     const float* sparse;  // [B][H][W] or null
     float* out;           // [B*C][H][W]
+    float* iter_out;      // kStoreSteps / kAdjoint: where the result of this pass's FIRST step goes ([B*C][H][W] plane) ...
+    long long iter_stride;  // ... and the (signed) distance in floats to the plane of the next step; the LAST step goes to `out`
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_bands, n_tasks;
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
@@ -333,9 +335,86 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
 }
 
+// What a launch computes with the folded weights w' it builds in its prologue:
+//   kForward     d <- c' + sum_k w'_k shift_k(d), `iters` times                                   (the product path)
+//   kStoreSteps  the same, and every step's result is also written to global memory (the forward iterates d_1..d_N
+//                that the backward pass needs)
+//   kAdjoint     lambda <- sum_k shift_{-k}(w'_k lambda), `iters` times, every step's result written out: the
+//                transpose of the forward step (cspn2d_bwd.cu has the derivation); `blur` carries lambda's start value
+enum ClusterMode { kForward = 0, kStoreSteps = 1, kAdjoint = 2 };
+
+// Adjoint of scatter_row: the SOURCE pixels (weights w, values l) of one row push w_k * l into the destination row DY
+// rows further down (off_k = (DY, dx)): destination column = source column + dx.  Columns -1 and PC belong to the
+// neighbouring lanes and are collected in xl / xr.
+template <int PC, int DY>
+__device__ __forceinline__ void adj_row(const float (&w)[PC][8], const float (&l)[PC], float (&acc)[PC], float& xl, float& xr) {
+#pragma unroll
+    for (int j = 0; j < PC; ++j) {
+#pragma unroll
+        for (int dx = 1; dx >= -1; --dx) {
+            if (DY == 0 && dx == 0) continue;
+            const int jd = j + dx;
+            const float wk = w[j][tap_of(DY, dx)];
+            if (jd < 0) xl = fmaf(wk, l[j], xl);
+            else if (jd >= PC) xr = fmaf(wk, l[j], xr);
+            else acc[jd] = fmaf(wk, l[j], acc[jd]);
+        }
+    }
+}
+// hand the out-of-thread columns to the neighbouring lanes: my xr is lane+1's column 0, my xl is lane-1's column PC-1
+template <int PC>
+__device__ __forceinline__ void fold_edges(float (&v)[PC], float xl, float xr, bool first_lane, bool last_lane) {
+    const float from_left = __shfl_up_sync(0xffffffffu, xr, 1);
+    const float from_right = __shfl_down_sync(0xffffffffu, xl, 1);
+    v[0] += first_lane ? 0.f : from_left;
+    v[PC - 1] += last_lane ? 0.f : from_right;
+}
+
+// One adjoint step lin = lambda_{t+1} -> lout = lambda_t.  The partial rows owed to the warps above / below depend on
+// lin only, so they are published FIRST (exchange buffer PAR) and the wait for the neighbours' rows comes last.
+template <int PR, int PC, int NW, int PAR>
+__device__ __forceinline__ void iterate_adj(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
+                                            const float (&lin)[PR][PC], float (&lout)[PR][PC]) {
+    using K = Cfg<PR, PC, NW>;
+    {
+        float up[PC], dn[PC], upl = 0.f, upr = 0.f, dnl = 0.f, dnr = 0.f;
+#pragma unroll
+        for (int j = 0; j < PC; ++j) { up[j] = 0.f; dn[j] = 0.f; }
+        adj_row<PC, -1>(w[0], lin[0], up, upl, upr);             // my top row feeds the row above my patch
+        adj_row<PC, +1>(w[PR - 1], lin[PR - 1], dn, dnl, dnr);   // my bottom row feeds the row below
+        fold_edges<PC>(up, upl, upr, x.first_lane, x.last_lane);
+        fold_edges<PC>(dn, dnl, dnr, x.first_lane, x.last_lane);
+        publish<PR, PC, NW, PAR>(x, wy, up, dn);
+    }
+    float xl[PR], xr[PR];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+        xl[r] = 0.f; xr[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < PC; ++j) lout[r][j] = 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {                               // source rows
+        if (r > 0) adj_row<PC, -1>(w[r], lin[r], lout[r - 1], xl[r - 1], xr[r - 1]);
+        adj_row<PC, 0>(w[r], lin[r], lout[r], xl[r], xr[r]);
+        if (r + 1 < PR) adj_row<PC, +1>(w[r], lin[r], lout[r + 1], xl[r + 1], xr[r + 1]);
+    }
+#pragma unroll
+    for (int r = 0; r < PR; ++r) fold_edges<PC>(lout[r], xl[r], xr[r], x.first_lane, x.last_lane);
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+    {
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
+        float a[PC], b[PC];
+        load_row_smem(p + (2 * wy) * K::TW, a);        // what the warp above owes my top row
+        load_row_smem(p + (2 * wy + 3) * K::TW, b);    // what the warp below owes my bottom row
+#pragma unroll
+        for (int j = 0; j < PC; ++j) { lout[0][j] += a[j]; lout[PR - 1][j] += b[j]; }
+    }
+}
+
 // GENERAL = false compiles out row bands and the continuation input of multi-pass plans: the common single-pass,
 // single-band launch (every BASELINE 2D config) pays nothing for them.
-template <int PR, int PC, int NW, bool ABS, bool GENERAL>
+template <int PR, int PC, int NW, bool ABS, bool GENERAL, int MODE = kForward>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
     using K = Cfg<PR, PC, NW>;
@@ -499,7 +578,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 cj[j] = in ? kappa * d[r][j] : 0.f;
             }
             // only this thread ever reads these values back: no barrier needed
-            store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);
+            if constexpr (MODE != kAdjoint) store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
             // a pass after the first continues from the previous pass's result; c' above still used d_0
             if (GENERAL && init != nullptr && col_in && y < H) {
                 const float4 iv = __ldg(reinterpret_cast<const float4*>(init + (size_t)bc * HW + (size_t)y * W + x_thr));
@@ -540,6 +619,47 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
         first = false;
         const int iters = prm.iters;
+        // kStoreSteps / kAdjoint: every step's result also goes to global memory (useful pixels only); the pass's last
+        // step leaves through the epilogue
+        [[maybe_unused]] float* step_ptr = nullptr;
+        [[maybe_unused]] unsigned step_rows = 0;      // bit r: row r of this thread is stored
+        if constexpr (MODE != kForward) {
+            const int sy0 = GENERAL ? prm.uy0[band] : 0, sy1 = GENERAL ? prm.uy1[band] : H;
+            if (x_thr >= prm.ux0[strip] && x_thr < prm.ux1[strip]) {
+#pragma unroll
+                for (int r = 0; r < PR; ++r)
+                    if (y_thr + r >= sy0 && y_thr + r < sy1) step_rows |= 1u << r;
+            }
+            step_ptr = prm.iter_out + (size_t)bc * HW + (size_t)y_thr * W + x_thr;
+        }
+        [[maybe_unused]] auto store_step = [&](const float (&v)[PR][PC]) {
+#pragma unroll
+            for (int r = 0; r < PR; ++r)
+                if (step_rows & (1u << r))
+                    *reinterpret_cast<float4*>(step_ptr + (size_t)r * W) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+            step_ptr += prm.iter_stride;
+        };
+        if constexpr (MODE == kAdjoint) {
+            float d2[PR][PC];               // (d -> d2) on even steps, back on odd ones
+            int it = 0;
+            for (; it + 2 <= iters; it += 2) {
+                iterate_adj<PR, PC, NW, 0>(xc, wy, ph0, w, d, d2);
+                ph0 ^= 1;
+                store_step(d2);
+                iterate_adj<PR, PC, NW, 1>(xc, wy, ph1, w, d2, d);
+                ph1 ^= 1;
+                if (it + 2 < iters) store_step(d);
+            }
+            if (it < iters) {
+                iterate_adj<PR, PC, NW, 0>(xc, wy, ph0, w, d, d2);
+                ph0 ^= 1;
+#pragma unroll
+                for (int r = 0; r < PR; ++r)
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
+            }
+            cluster_arrive_relaxed();
+        } else {
 #ifndef CSPN_ABLATE_NO_SYNC
         publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
 #endif
@@ -553,12 +673,15 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
             iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
+            if constexpr (MODE == kStoreSteps) store_step(d2);
             iterate<PR, PC, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
+            if constexpr (MODE == kStoreSteps) store_step(d);
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
             iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
+            if constexpr (MODE == kStoreSteps) store_step(d2);
             iterate<PR, PC, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         } else if (iters - it == 1) {
@@ -572,6 +695,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
                 for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
         }
+        }   // MODE != kAdjoint
 
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
@@ -581,8 +705,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
             for (int r = 0; r < PR; ++r) {
                 const int y = y_thr + r;
-                if (y >= uy0 && y < uy1)
-                    __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x_thr), make_float4(d[r][0], d[r][1], d[r][2], d[r][3]));
+                if (y >= uy0 && y < uy1) {
+                    const float4 v = make_float4(d[r][0], d[r][1], d[r][2], d[r][3]);
+                    if constexpr (MODE == kForward) __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x_thr), v);
+                    else *reinterpret_cast<float4*>(out + (size_t)y * W + x_thr) = v;   // read again by the next pass
+                }
             }
         }
     }
@@ -594,7 +721,9 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
 struct KernelCfg {
     int PR, PC, NW;
-    const void* fn[2][2];  // [general][norm_abs]
+    const void* fn[2][2];      // kForward: [general][norm_abs]
+    const void* fn_steps[2];   // kStoreSteps [norm_abs]
+    const void* fn_adj[2];     // kAdjoint    [norm_abs]
     size_t smem;
     int RB() const { return PR * NW; }
     int TW() const { return 32 * PC; }
@@ -605,6 +734,10 @@ KernelCfg make_cfg() {
     return KernelCfg{PR, PC, NW,
                      {{(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, false>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, false>},
                       {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, true>, (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true>}},
+                     {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, true, kStoreSteps>,
+                      (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true, kStoreSteps>},
+                     {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, true, kAdjoint>,
+                      (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true, kAdjoint>},
                      Cfg<PR, PC, NW>::kSmemBytes};
 }
 
@@ -660,9 +793,10 @@ int max_active_clusters(int ci, int cs, int dev) {
         if (e.first.cfg == ci && e.first.cs == cs && e.first.dev == dev) return e.second;
     const KernelCfg& k = configs()[ci];
     if (!g_attr_set[dev & 15][ci]) {
-        for (int ab = 0; ab < 4; ++ab)
-            if (cudaFuncSetAttribute(k.fn[ab >> 1][ab & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
-                cudaFuncSetAttribute(k.fn[ab >> 1][ab & 1], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        const void* all[8] = {k.fn[0][0], k.fn[0][1], k.fn[1][0], k.fn[1][1], k.fn_steps[0], k.fn_steps[1], k.fn_adj[0], k.fn_adj[1]};
+        for (const void* f : all)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
+                cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                 cudaGetLastError();
                 return 0;
             }
@@ -897,84 +1031,136 @@ int cluster2d_plan_json(int H, int W, int iters, char* buf, int len) {
     return n;
 }
 
-int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {
+namespace {
+
+int plan_for_launch(const Problem2D& p, Plan& plan) {
     int dev = 0;
     CSPN_CUDA_TRY(cudaGetDevice(&dev));
-    Plan plan;
-    {
-        std::lock_guard<std::mutex> lock(g_mu);
-        char why[200] = "";
-        if (!make_plan(p.H, p.W, p.iters, dev, plan, why, sizeof(why))) {
-            set_error("cluster kernel unsupported: %s", why);
-            return CSPN_ERR_UNSUPPORTED;
-        }
-        int rc = get_encode();
-        if (rc != CSPN_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    char why[200] = "";
+    if (!make_plan(p.H, p.W, p.iters, dev, plan, why, sizeof(why))) {
+        set_error("cluster kernel unsupported: %s", why);
+        return CSPN_ERR_UNSUPPORTED;
     }
+    return get_encode();
+}
+
+// One pass = one launch of `fn` with plan `pp`.  `start` plays the role of blur_depth (kAdjoint: lambda's start value),
+// `init` continues from an earlier pass (kForward / kStoreSteps), `iter_out` / `iter_stride` say where every step but
+// the last is written (kStoreSteps / kAdjoint), the last step goes to `out`.
+int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const float* start, const float* init, float* out,
+                float* iter_out, long long iter_stride, cudaStream_t stream) {
+    const KernelCfg& k = configs()[pp.cfg];
+    // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
+    CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H,
+                  p.B * p.gch, k.TW(), k.RB());
+        return CSPN_ERR_CUDA;
+    }
+    ClusterParams prm;
+    prm.blur = start; prm.init = init; prm.sparse = p.sparse; prm.out = out;
+    prm.iter_out = iter_out; prm.iter_stride = iter_stride;
+    prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = pp.iters; prm.norm_abs = p.norm_abs;
+    prm.n_strips = pp.n_strips;
+    prm.n_bands = pp.n_bands;
+    const long tasks = (long)p.B * p.C * pp.n_strips * pp.n_bands;
+    if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
+    prm.n_tasks = (int)tasks;
+    for (int i = 0; i < kMaxStrips; ++i) {
+        const bool in = i < pp.n_strips;
+        prm.tile_x0[i] = in ? pp.tile_x0[i] : 0; prm.ux0[i] = in ? pp.ux0[i] : 0; prm.ux1[i] = in ? pp.ux1[i] : 0;
+    }
+    for (int i = 0; i < kMaxBands; ++i) {
+        const bool in = i < pp.n_bands;
+        prm.band_y0[i] = in ? pp.band_y0[i] : 0; prm.uy0[i] = in ? pp.uy0[i] : 0; prm.uy1[i] = in ? pp.uy1[i] : 0;
+    }
+    // persistent clusters: as many as fit on the device at once, each looping over tasks
+    const long n_clusters = tasks < pp.max_clusters ? tasks : pp.max_clusters;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * pp.cs));
+    cfg.blockDim = dim3(32 * k.NW);
+    cfg.dynamicSmemBytes = k.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pp.cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void* args[2] = {(void*)&tm, (void*)&prm};
+    CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
+    return CSPN_OK;
+}
+
+}  // namespace
+
+int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {
+    Plan plan;
+    int rc = plan_for_launch(p, plan);
+    if (rc != CSPN_OK) return rc;
     const size_t d_bytes = (size_t)p.B * p.C * p.H * p.W * sizeof(float);
     if (plan.n_pass > 1 && (!ws || ws_bytes < d_bytes)) {
         set_error("cluster path splits %d steps into %d passes and needs %zu workspace bytes, got %zu", p.iters, plan.n_pass,
                   d_bytes, ws ? ws_bytes : (size_t)0);
         return CSPN_ERR_WORKSPACE;
     }
-
-    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
-    const cuuint32_t estr[3] = {1, 1, 1};
     const float* prev = nullptr;   // result of the previous pass
     for (int ip = 0; ip < plan.n_pass; ++ip) {
         const PassPlan& pp = plan.pass(ip);
-        const KernelCfg& k = configs()[pp.cfg];
-        // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane
-        CUtensorMap tm;
-        const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
-        CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H,
-                      p.B * p.gch, k.TW(), k.RB());
-            return CSPN_ERR_CUDA;
-        }
         // passes alternate between the workspace and `out` such that the last one lands in `out`
         float* dst = ((plan.n_pass - 1 - ip) & 1) ? static_cast<float*>(ws) : p.out;
-
-        ClusterParams prm;
-        prm.blur = p.blur; prm.init = prev; prm.sparse = p.sparse; prm.out = dst;
-        prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = pp.iters; prm.norm_abs = p.norm_abs;
-        prm.n_strips = pp.n_strips;
-        prm.n_bands = pp.n_bands;
-        const long tasks = (long)p.B * p.C * pp.n_strips * pp.n_bands;
-        if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
-        prm.n_tasks = (int)tasks;
-        for (int i = 0; i < kMaxStrips; ++i) {
-            const bool in = i < pp.n_strips;
-            prm.tile_x0[i] = in ? pp.tile_x0[i] : 0; prm.ux0[i] = in ? pp.ux0[i] : 0; prm.ux1[i] = in ? pp.ux1[i] : 0;
-        }
-        for (int i = 0; i < kMaxBands; ++i) {
-            const bool in = i < pp.n_bands;
-            prm.band_y0[i] = in ? pp.band_y0[i] : 0; prm.uy0[i] = in ? pp.uy0[i] : 0; prm.uy1[i] = in ? pp.uy1[i] : 0;
-        }
-        // persistent clusters: as many as fit on the device at once, each looping over tasks
-        const long n_clusters = tasks < pp.max_clusters ? tasks : pp.max_clusters;
-
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(n_clusters * pp.cs));
-        cfg.blockDim = dim3(32 * k.NW);
-        cfg.dynamicSmemBytes = k.smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = pp.cs;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        void* args[2] = {(void*)&tm, (void*)&prm};
         const bool general = pp.n_bands > 1 || prev != nullptr;
-        CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn[general ? 1 : 0][p.norm_abs ? 1 : 0], args));
+        rc = launch_pass(p, pp, configs()[pp.cfg].fn[general ? 1 : 0][p.norm_abs ? 1 : 0], p.blur, prev, dst, nullptr, 0, stream);
+        if (rc != CSPN_OK) return rc;
         ++*launches;
         prev = dst;
+    }
+    return CSPN_OK;
+}
+
+// The forward again, keeping every iterate: steps[t] = d_{t+1} for t = 0..N-1 (planes of B*C*H*W floats).
+int cluster2d_forward_steps(const Problem2D& p, float* steps, cudaStream_t stream, int* launches) {
+    Plan plan;
+    int rc = plan_for_launch(p, plan);
+    if (rc != CSPN_OK) return rc;
+    const long long n = (long long)p.B * p.C * p.H * p.W;
+    int done = 0;
+    for (int ip = 0; ip < plan.n_pass; ++ip) {
+        const PassPlan& pp = plan.pass(ip);
+        rc = launch_pass(p, pp, configs()[pp.cfg].fn_steps[p.norm_abs ? 1 : 0], p.blur, done ? steps + (done - 1) * n : nullptr,
+                         steps + (done + pp.iters - 1) * n, steps + done * n, n, stream);
+        if (rc != CSPN_OK) return rc;
+        ++*launches;
+        done += pp.iters;
+    }
+    return CSPN_OK;
+}
+
+// The adjoint sweep: lam[t] = lambda_t for t = N-1 .. 0, starting from lambda_N = grad_out.
+int cluster2d_adjoint_steps(const Problem2D& p, const float* grad_out, float* lam, cudaStream_t stream, int* launches) {
+    Plan plan;
+    int rc = plan_for_launch(p, plan);
+    if (rc != CSPN_OK) return rc;
+    const long long n = (long long)p.B * p.C * p.H * p.W;
+    const int N = p.iters;
+    int done = 0;   // adjoint steps taken so far: lambda_{N-done} is the current state
+    for (int ip = 0; ip < plan.n_pass; ++ip) {
+        const PassPlan& pp = plan.pass(ip);
+        rc = launch_pass(p, pp, configs()[pp.cfg].fn_adj[p.norm_abs ? 1 : 0], done ? lam + (long long)(N - done) * n : grad_out, nullptr,
+                         lam + (long long)(N - done - pp.iters) * n, lam + (long long)(N - done - 1) * n, -n, stream);
+        if (rc != CSPN_OK) return rc;
+        ++*launches;
+        done += pp.iters;
     }
     return CSPN_OK;
 }

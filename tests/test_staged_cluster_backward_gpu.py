@@ -1,0 +1,50 @@
+"""STAGED: the register-resident backward (CSPN_B200_BWD=cluster, cspn2d_bwd.cu) was written after round 1's GPU budget
+was spent and has not run on hardware yet, so these tests are opt-in: CSPN_B200_TEST_STAGED=1 pytest -m gpu ...
+They compare it with fp64 autograd through the reference's op sequence and with the validated launch-per-step path."""
+import os
+
+import pytest
+import torch
+
+import cspn_b200
+from cspn_b200 import _lib
+from cspn_b200.synth import make_inputs
+from oracle import cspn_torch_port as tp
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('CSPN_B200_TEST_STAGED') != '1', reason='staged path: opt-in until validated on a B200')]
+
+
+def grads(g, d, s, go, n, norm):
+    gc = g.cuda().requires_grad_(True)
+    dc = d.cuda().requires_grad_(True)
+    cspn_b200.Affinity_Propagate(n, 3, norm)(gc, dc, None if s is None else s.cuda()).backward(go.cuda())
+    torch.cuda.synchronize()
+    return gc.grad.double().cpu(), dc.grad.double().cpu(), _lib.lib().cspn_last_launches()
+
+
+@pytest.mark.parametrize('norm', ['8sum', '8sum_abs'])
+@pytest.mark.parametrize('shape,n,sparse', [
+    ((2, 1, 12, 16), 5, 'signed'),       # one CTA, one strip
+    ((1, 2, 48, 132), 6, 'bernoulli'),   # channels share the affinity; two strips
+    ((1, 1, 100, 260), 24, 'bernoulli'),  # several CTAs per cluster: DSMEM partial rows
+    ((1, 1, 40, 264), 40, None),         # multi-pass plan
+    ((1, 1, 700, 64), 4, 'signed'),      # row bands
+])
+def test_staged_cluster_backward_matches_reference_autograd(shape, n, sparse, norm, monkeypatch):
+    B, C, H, W = shape
+    g, d, s = make_inputs(31 + H, B, C, H, W, 9, sparse, 25)
+    go = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(1))
+    g64 = g.double().requires_grad_(True)
+    d64 = d.double().requires_grad_(True)
+    tp.cspn2d_torch(g64, d64, None if s is None else s.double(), n, norm).backward(go.double())
+    base_g, base_d, base_launches = grads(g, d, s, go, n, norm)
+    monkeypatch.setenv('CSPN_B200_BWD', 'cluster')
+    new_g, new_d, new_launches = grads(g, d, s, go, n, norm)
+    assert new_launches < base_launches                      # it really took the cluster formulation
+    for ours, theirs, name in ((new_g, g64.grad, 'guidance'), (new_d, d64.grad, 'blur')):
+        scale = theirs.abs().mean()
+        err = (ours - theirs).abs()
+        assert (err <= 2e-3 * (theirs.abs() + scale)).all(), (name, float(err.max()), float(scale))
+    assert torch.allclose(new_g, base_g, rtol=1e-3, atol=1e-4 * float(base_g.abs().mean()))
+    assert torch.allclose(new_d, base_d, rtol=1e-3, atol=1e-4 * float(base_d.abs().mean()))
