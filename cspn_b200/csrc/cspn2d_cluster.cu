@@ -66,9 +66,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -132,11 +129,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
                      remote_addr),
                  "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
-                 : "memory");
-}
-__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, float2 v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
-                 "f"(v.x), "f"(v.y), "r"(remote_bar)
                  : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
@@ -1023,9 +1015,9 @@ int cluster2d_plan_json(int H, int W, int iters, char* buf, int len) {
         put("%s{\"count\": %d, \"iters\": %d, \"PR\": %d, \"NW\": %d, \"RB\": %d, \"TW\": %d, \"cs\": %d, \"max_clusters\": %d, \"strips\": [",
             (part == 1 && plan.n_long > 0) ? ", " : "", count, pp.iters, k.PR, k.NW, k.RB(), k.TW(), pp.cs, pp.max_clusters);
         for (int i = 0; i < pp.n_strips; ++i) put("%s[%d, %d, %d]", i ? ", " : "", pp.tile_x0[i], pp.ux0[i], pp.ux1[i]);
-        put("], \"bands\": [");
+        put("%s", "], \"bands\": [");
         for (int i = 0; i < pp.n_bands; ++i) put("%s[%d, %d, %d]", i ? ", " : "", pp.band_y0[i], pp.uy0[i], pp.uy1[i]);
-        put("]}");
+        put("%s", "]}");
     }
     if (n < len) n += snprintf(buf + n, len - n, "]}");
     return n;
