@@ -53,11 +53,17 @@ def up_to_date():
             and open(STAMP).read().strip() == _digest())
 
 
-def build(force=False, verbose=False):
-    """Compiles every .cu under csrc/ (separately, in parallel) and links the shared library."""
-    if not force and up_to_date():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compiles every .cu under csrc/ (separately, in parallel) and links the shared library.
+
+    `defines` / `out` build an experimental variant (e.g. -DCSPN_EARLY_PUBLISH) into another file, to be loaded with
+    CSPN_B200_LIB=<out>; the product library and its stamp are not touched."""
+    variant = bool(defines) or out is not None
+    lib = os.path.abspath(out) if out else LIB
+    obj_dir = os.path.join(os.path.dirname(lib), os.path.basename(lib) + '.obj') if variant else OUT_DIR
+    if not variant and not force and up_to_date():
         return LIB
-    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     env = dict(os.environ)
     # the image exports CC=/opt/gcc/bin/gcc; nvcc wants the system g++ as host compiler
@@ -65,27 +71,35 @@ def build(force=False, verbose=False):
     procs = []
     objs = []
     for src in _sources():
-        obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + '.o')
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + ['-Xptxas', '-v', '-c', src, '-o', obj]
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-Xptxas', '-v', '-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, text=True)))
     log = []
     for src, p in procs:
-        out, _ = p.communicate()
-        log.append(f'== {os.path.basename(src)}\n{out}')
+        out_text, _ = p.communicate()
+        log.append(f'== {os.path.basename(src)}\n{out_text}')
         if p.returncode != 0:
             sys.stderr.write('\n'.join(log))
             raise RuntimeError(f'nvcc failed on {src}')
-    with open(os.path.join(OUT_DIR, 'ptxas.log'), 'w') as fh:
+    with open(os.path.join(obj_dir, 'ptxas.log'), 'w') as fh:
         fh.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
-    link = [nvcc] + ccbin + ['-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs
+    link = [nvcc] + ccbin + ['-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', lib] + objs
     subprocess.check_call(link, env=env)
-    with open(STAMP, 'w') as fh:
-        fh.write(_digest())
-    return LIB
+    if not variant:
+        with open(STAMP, 'w') as fh:
+            fh.write(_digest())
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    import argparse
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument('--force', action='store_true')
+    ap.add_argument('-v', dest='verbose', action='store_true')
+    ap.add_argument('--define', action='append', default=[], help='extra -D for an experimental variant (repeatable)')
+    ap.add_argument('--out', help='output .so of the variant (use with CSPN_B200_LIB)')
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose, defines=tuple(a.define), out=a.out))

@@ -516,6 +516,19 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             m[r][0] = signf(sv.x); m[r][1] = signf(sv.y); m[r][2] = signf(sv.z); m[r][3] = signf(sv.w);
         }
 
+        // Build-time experiment for the next tuning round (-DCSPN_EARLY_PUBLISH, off by default, not yet measured): the
+        // first row exchange of a task only needs blur_depth, so it can be issued before the prologue and its DSMEM
+        // round trip hides under the ~2.5 us of normalisation instead of stalling the first step.
+#ifdef CSPN_EARLY_PUBLISH
+        constexpr bool kEarlyPublish = (MODE == kForward) && !GENERAL;
+#else
+        constexpr bool kEarlyPublish = false;
+#endif
+        if constexpr (kEarlyPublish) {
+            if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
+            publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+        }
+
         mbar_wait(bar_tma, ph_tma);
         ph_tma ^= 1;
 
@@ -608,7 +621,9 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         }
 
         // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
-        if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
+        if constexpr (!kEarlyPublish) {
+            if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
+        }
         first = false;
         const int iters = prm.iters;
         // kStoreSteps / kAdjoint: every step's result also goes to global memory (useful pixels only); the pass's last
@@ -653,7 +668,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             cluster_arrive_relaxed();
         } else {
 #ifndef CSPN_ABLATE_NO_SYNC
-        publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+        if constexpr (!kEarlyPublish) publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
 #endif
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
