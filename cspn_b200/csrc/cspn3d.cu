@@ -79,7 +79,14 @@ step3d_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const 
 // Vectorised step for W % 4 == 0: one thread produces 4 consecutive voxels of a row.  The 27 weight planes stream
 // through as LDG.128 (they are the HBM traffic of this path: 108 B per voxel and step), the 9 neighbouring rows of the
 // current volume are read as one aligned float4 plus two edge scalars each (L1/L2 hits).
-__global__ void __launch_bounds__(128)
+// CSPN3D_MIN_BLOCKS: build-time knob for the next tuning round (python -m cspn_b200.build --define CSPN3D_MIN_BLOCKS=8
+// caps the kernel at 64 registers -> 32 instead of 24 resident warps per SM); unset = ptxas' own choice (75 registers).
+#ifdef CSPN3D_MIN_BLOCKS
+#define CSPN3D_BOUNDS __launch_bounds__(128, CSPN3D_MIN_BLOCKS)
+#else
+#define CSPN3D_BOUNDS __launch_bounds__(128)
+#endif
+__global__ void CSPN3D_BOUNDS
 step3d_vec4_kernel(const float* __restrict__ wk, const float* __restrict__ d0, const float* __restrict__ cur,
                    float* __restrict__ dst, int C, int D, int H, int W) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
