@@ -91,3 +91,19 @@ def test_product_package_never_imports_the_oracle():
             text = open(os.path.join(dirpath, f)).read()
             assert not re.search(r'^\s*(from|import)\s+oracle', text, re.M), f'{f} imports the oracle'
             assert 'libcspn_oracle' not in text and 'c_oracle' not in text, f'{f} loads the oracle library'
+
+
+def test_c_consumer_of_the_abi_compiles_and_runs_without_a_gpu(tmp_path):
+    """examples/c_abi_demo.c: a plain-C front-end (dlopen + the header) sees the same contract as the ctypes binding."""
+    import shutil
+    import subprocess
+    cc = '/usr/bin/gcc' if os.path.isfile('/usr/bin/gcc') else shutil.which('gcc')
+    if cc is None:
+        pytest.skip('no C compiler')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'c_abi_demo')
+    subprocess.check_call([cc, '-Wall', '-Werror', '-I', os.path.join(root, 'include'),
+                           os.path.join(root, 'examples', 'c_abi_demo.c'), '-o', exe, '-ldl'])
+    out = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'cluster: patch 5x4' in out.stdout and 'status -1' in out.stdout
