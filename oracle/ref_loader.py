@@ -45,3 +45,16 @@ def reference_forward(guidance, blur_depth, sparse_depth, prop_time, norm_type):
     layer = mod.Affinity_Propagate(prop_time, 3, norm_type)
     with torch.no_grad(), cuda_identity_shim():
         return layer(guidance, blur_depth, sparse_depth)
+
+
+def reference_gradients(guidance, blur_depth, sparse_depth, grad_out, prop_time, norm_type):
+    """autograd through the reference module itself (what train.py:196-199 differentiates): returns
+    (out, d out / d guidance . grad_out, d out / d blur_depth . grad_out) as torch tensors."""
+    mod = load_reference()
+    layer = mod.Affinity_Propagate(prop_time, 3, norm_type)
+    g = guidance.clone().requires_grad_(True)
+    d = blur_depth.clone().requires_grad_(True)
+    with cuda_identity_shim():
+        out = layer(g, d, sparse_depth)
+        out.backward(grad_out)
+    return out.detach(), g.grad, d.grad

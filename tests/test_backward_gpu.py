@@ -1,11 +1,16 @@
 """GPU test of the native adjoint (cspn2d_bwd_f32) against autograd through the reference's op sequence
 (oracle/cspn_torch_port.py, bit-identical to cspn.py on the forward).  Called through the nn.Module, i.e. the way
 train.py:196-199 uses the operator."""
+import glob
+import os
+
+import numpy as np
 import pytest
 import torch
 
 import cspn_b200
 from cspn_b200.synth import make_inputs
+from conftest import GOLDEN_DIR
 from oracle import cspn_torch_port as tp
 
 pytestmark = pytest.mark.gpu
@@ -35,6 +40,25 @@ def test_gradients_match_reference_autograd(shape, n, sparse, norm):
         err = (ours - theirs).abs()
         assert (err <= 2e-3 * (theirs.abs() + scale)).all(), (name, float(err.max()), float(scale))
     assert torch.count_nonzero(gc.grad[:, 8:]) == 0            # unused guidance channels get zero gradient
+
+
+GRAD_GOLDENS = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, 'grads', '*.npz')))
+
+
+@pytest.mark.parametrize('name', GRAD_GOLDENS)
+def test_gradients_match_the_reference_modules_own_autograd(name):
+    """tests/golden/grads: gradients from autograd through the unmodified reference module (fp32, as train.py runs it)."""
+    z = np.load(os.path.join(GOLDEN_DIR, 'grads', name + '.npz'))
+    gc = torch.tensor(z['guidance']).cuda().requires_grad_(True)
+    dc = torch.tensor(z['blur']).cuda().requires_grad_(True)
+    s = torch.tensor(z['sparse_depth']).cuda() if 'sparse_depth' in z else None
+    out = cspn_b200.Affinity_Propagate(int(z['prop_time']), 3, str(z['norm_type']))(gc, dc, s)
+    out.backward(torch.tensor(z['grad_out']).cuda())
+    for ours, ref, what in ((gc.grad, z['grad_guidance'], 'guidance'), (dc.grad, z['grad_blur'], 'blur')):
+        ours = ours.cpu().numpy()
+        scale = np.abs(ref).mean()
+        err = np.abs(ours - ref)
+        assert (err <= 3e-3 * (np.abs(ref) + scale)).all(), (what, float(err.max()), float(scale))
 
 
 def test_training_step_through_the_module():
