@@ -52,6 +52,8 @@ struct ClusterParams {
     long long iter_stride;  // ... and the (signed) distance in floats to the plane of the next step; the LAST step goes to `out`
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_bands, n_tasks;
+    int zero;             // always 0; a value ptxas cannot fold (see wait_token)
+    unsigned long long* trace;   // -DCSPN_TRACE builds only (tools/trace_cluster.py): per-warp clock stamps, else null
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -89,6 +91,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
+}
+// The first probe carries no dependency (ptxas issues it early, its latency overlaps the FMAs behind it); the decision
+// to go on is what depends on `token` (a run-time zero derived from accumulators, see wait_token).
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+__device__ __forceinline__ void mbar_wait_dep(uint32_t bar, uint32_t parity, uint32_t token) {
+    uint32_t done = mbar_try(bar, parity) | token;
+    while (!done) done = mbar_try(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -159,9 +180,12 @@ struct Cfg {
     static constexpr int TW = 32 * PC;   // tile (strip) width
     static constexpr int TWP = TW + 8;   // staged row pitch: 4 apron columns on each side
     static constexpr int kSlots = 2 * NW + 2;
+    // exchange rows carry 4 zero floats on each side: a thread reads the x-neighbours of a halo row straight from the
+    // row (lane 0 / 31 find the zeros), so the halo taps need neither shuffles nor selects
+    static constexpr int TWX = TW + 8;
     static constexpr size_t kPlaneBytes = (size_t)RB * TWP * sizeof(float);
     static constexpr size_t kStageBytes = 8 * kPlaneBytes;
-    static constexpr size_t kXchParityBytes = (size_t)kSlots * TW * sizeof(float);
+    static constexpr size_t kXchParityBytes = (size_t)kSlots * TWX * sizeof(float);
     static constexpr size_t kXchBytes = 2 * kXchParityBytes;
     // the folded constant term c' (one float per pixel) lives in shared memory: it is read once per pixel and
     // iteration (one LDS.128 per patch row), which frees PR*PC registers per thread
@@ -176,7 +200,7 @@ struct Cfg {
 
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));   // 1/0 = inf, so 0 * (1/0) = NaN like the reference's 0/0
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));   // 1/0 = inf, so 0 * (1/0) = NaN like the reference's 0/0; subnormal x: see exact_div
     return r;
 }
 
@@ -236,8 +260,23 @@ __device__ __forceinline__ void store_row_remote(uint32_t addr, const float (&v)
     st_async_v4(addr, make_float4(v[0], v[1], v[2], v[3]), bar);
 }
 
+// -DCSPN_TRACE: clock stamps of cluster 0's tasks 1..kTraceTasks (steady state), lane 0 of every warp:
+// trace[((slot*16 + cta)*8 + warp)*kTraceEvents + event].  Events: 0 task start, 1 guidance landed, 2 prologue done,
+// 3 staging buffer released, 4 exchange buffers free, 5+3t / 6+3t / 7+3t = step t before wait / after wait / after
+// publish, kTraceEvents-2 loop done, kTraceEvents-1 stored.
+constexpr int kTraceTasks = 4, kTraceEvents = 5 + 3 * 64 + 2;
+#ifdef CSPN_TRACE
+#define CSPN_STAMP(xc, ev) do { if ((xc).tr) (xc).tr[(ev)] = clock64(); } while (0)
+#else
+#define CSPN_STAMP(xc, ev) do { } while (0)
+#endif
+
 // Per-thread constants of the row exchange.
 struct Xch {
+#ifdef CSPN_TRACE
+    unsigned long long* tr;   // this warp's stamp row of the current task (lane 0, traced tasks only), else null
+    int step;                 // running step index of the traced task
+#endif
     float* base;          // xch + lane*PC (parity 0, slot 0)
     uint32_t bar_full0;   // local mbarriers: full[0], full[1] = full[0] + 8
     uint32_t rx_bytes;    // halo bytes this CTA receives per exchange
@@ -250,16 +289,31 @@ struct Xch {
     bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
+    uint32_t zero;        // 0 at run time, opaque at compile time
 };
+
+// -DCSPN_WAIT_DEP: a zero that DEPENDS on the given accumulators, added to the barrier address: the mbarrier wait cannot be
+// scheduled before the FMAs that produce them (ptxas otherwise sinks the pre-wait FMAs below the wait).
+template <int PC>
+__device__ __forceinline__ uint32_t wait_token(const Xch& x, const float (&a)[PC], const float (&b)[PC]) {
+#ifdef CSPN_WAIT_DEP
+    uint32_t t = 0;
+#pragma unroll
+    for (int j = 0; j < PC; ++j) t |= __float_as_uint(a[j]) | __float_as_uint(b[j]);
+    return t & x.zero;
+#else
+    return 0u;
+#endif
+}
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
 // halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
 template <int PR, int PC, int NW, int PAR>
 __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)[PC], const float (&bot)[PC]) {
     using K = Cfg<PR, PC, NW>;
-    float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
-    store_row_smem(p + (1 + 2 * wy) * K::TW, top);
-    store_row_smem(p + (2 + 2 * wy) * K::TW, bot);
+    float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
+    store_row_smem(p + (1 + 2 * wy) * K::TWX, top);
+    store_row_smem(p + (2 + 2 * wy) * K::TWX, bot);
     const uint32_t bar = x.bar_full0 + 8 * PAR;
     // my top row is the "halo from below" (last slot) of the CTA above; my bottom row the "halo from above" below
     // (remote_up / remote_dn are warp-uniform by construction -- wy comes from a shuffle -- so these are uniform
@@ -295,13 +349,15 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     }
     // ---- the neighbours' rows ----------------------------------------------------------------------------
 #ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
+    CSPN_STAMP(x, 5 + 3 * x.step);
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
+    CSPN_STAMP(x, 6 + 3 * x.step);
 #endif
     {
-        const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
         float u[PC], ue[2], d[PC], de[2];
-        load_row_smem(p + (2 * wy) * K::TW, u);        // row above my patch
-        load_row_smem(p + (2 * wy + 3) * K::TW, d);    // row below my patch
+        load_row_smem(p + (2 * wy) * K::TWX, u);        // row above my patch
+        load_row_smem(p + (2 * wy + 3) * K::TWX, d);    // row below my patch
         row_edges<PC>(u, ue, x.first_lane, x.last_lane);
         row_edges<PC>(d, de, x.first_lane, x.last_lane);
         scatter_row<PC, -1>(w[0], Row<PC>{u, ue}, dout[0]);
@@ -318,6 +374,7 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
     if constexpr (PUBLISH) {
 #ifndef CSPN_ABLATE_NO_SYNC
         publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+        CSPN_STAMP(x, 7 + 3 * x.step);
 #endif
         // ---- tail: seed the next step's accumulators, x-edges of the new rows ---------------------------------
 #pragma unroll
@@ -325,6 +382,194 @@ __device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, co
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
     }
+}
+
+// ---- step, second formulation (-DCSPN_STEP=2) ------------------------------------------------------------------
+// Same arithmetic, different critical path.  What a neighbour waits for is my new boundary rows; what they wait for is
+// the neighbours' previous boundary rows.  So: (A) every tap fed by one of my OWN rows -- 136 of the 160 FMAs -- goes
+// before the mbarrier wait, interior rows are complete there and their x-edges are shuffled at once; (B) after the wait
+// only the two halo rows remain: their x-neighbours are read from the padded exchange row itself (no shuffle, no
+// select in the chain wait -> LDS -> 3 FMA -> STS), and the boundary rows are published immediately; (C) the tail
+// shuffles the two boundary rows and re-seeds the dead register set with c'.
+// Tile-edge lanes: the shuffled-in value of lane 0 (31) is meaningless; instead of zeroing it with a select per row
+// and step, the three taps that would consume it are predicated off (exactly the reference's zero padding, NaN-safe).
+template <int PC, int SRC_DY, bool GUARD, typename Src>
+__device__ __forceinline__ void scatter_row2(const float (&w)[PC][8], const Src& src, float (&acc)[PC], bool use_left,
+                                             bool use_right) {
+#pragma unroll
+    for (int jx = 0; jx <= PC + 1; ++jx) {
+        const int sx = jx <= PC - 1 ? jx : (jx == PC ? -1 : PC);   // own columns first, then the left / right neighbour
+        const float xv = src(sx);
+#pragma unroll
+        for (int dx = 1; dx >= -1; --dx) {
+            const int j = sx - dx;
+            if (j < 0 || j >= PC) continue;
+            if (SRC_DY == 0 && dx == 0) continue;
+            if (GUARD && sx < 0) { if (use_left) acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]); }
+            else if (GUARD && sx >= PC) { if (use_right) acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]); }
+            else acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]);
+        }
+    }
+}
+// The taps one source value `xv` (column sx of a row SRC_DY rows below the destination row) feeds in that destination row.
+template <int PC, int SRC_DY>
+__device__ __forceinline__ void taps_of_source(const float (&w)[PC][8], int sx, float xv, float (&acc)[PC], bool use_left,
+                                               bool use_right) {
+#pragma unroll
+    for (int dx = 1; dx >= -1; --dx) {
+        const int j = sx - dx;
+        if (j < 0 || j >= PC) continue;
+        if (SRC_DY == 0 && dx == 0) continue;
+        if (sx < 0) { if (use_left) acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]); }
+        else if (sx >= PC) { if (use_right) acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]); }
+        else acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]);
+    }
+}
+template <int PC>
+__device__ __forceinline__ void row_edges_raw(const float (&v)[PC], float (&ed)[2]) {
+    ed[0] = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);     // lane 0 gets its own value back: never consumed (guarded taps)
+    ed[1] = __shfl_down_sync(0xffffffffu, v[0], 1);
+}
+
+template <int PR, int PC, int NW, int PAR, bool PUBLISH>
+__device__ __forceinline__ void iterate2(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
+                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
+                                         float (&eout)[PR][2]) {
+    using K = Cfg<PR, PC, NW>;
+    const bool ul = !x.first_lane, ur = !x.last_lane;
+    // ---- A: own source rows ----------------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+        if (r > 0) scatter_row2<PC, -1, true>(w[r], Row<PC>{din[r - 1], ein[r - 1]}, dout[r], ul, ur);
+        scatter_row2<PC, 0, true>(w[r], Row<PC>{din[r], ein[r]}, dout[r], ul, ur);
+        if (r + 1 < PR) scatter_row2<PC, +1, true>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r], ul, ur);
+        if (PUBLISH && r > 0 && r + 1 < PR) row_edges_raw<PC>(dout[r], eout[r]);   // interior row r is final
+    }
+    // ---- B: the neighbours' rows -------------------------------------------------------------------------------
+#ifndef CSPN_ABLATE_NO_SYNC
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+#endif
+    {
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
+        const float* pu = p + (2 * wy) * K::TWX;          // row above my patch
+        const float* pd = p + (2 * wy + 3) * K::TWX;      // row below my patch
+        float u[PC], ue[2], d[PC], de[2];
+        load_row_smem(pu, u);
+        load_row_smem(pd, d);
+        ue[0] = pu[-1]; ue[1] = pu[PC];                   // pad floats are zero at the tile edges
+        de[0] = pd[-1]; de[1] = pd[PC];
+        scatter_row2<PC, -1, false>(w[0], Row<PC>{u, ue}, dout[0], true, true);
+        scatter_row2<PC, +1, false>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1], true, true);
+    }
+    if constexpr (PUBLISH) {
+#ifndef CSPN_ABLATE_NO_SYNC
+        publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+#endif
+        // ---- C: tail ------------------------------------------------------------------------------------------
+        row_edges_raw<PC>(dout[0], eout[0]);
+        row_edges_raw<PC>(dout[PR - 1], eout[PR - 1]);
+#pragma unroll
+        for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
+    }
+}
+
+// ---- step, third formulation (-DCSPN_STEP=3): the second one with the ORDER pinned -----------------------------------
+// ptxas schedules register arithmetic freely around the (volatile) barrier instructions, and left to itself it sinks most
+// of the FMAs between the wait and the publish.  Memory operations, however, keep their order relative to the volatile
+// asm statements: the accumulators of the interior rows are therefore seeded with c' (an LDS) only AFTER the publish, so
+// none of their 96 FMAs can run before it.  Per step: wait -> 24 halo FMAs -> publish -> [96 interior FMAs of this step,
+// then the 40 own-row FMAs of the next step's boundary rows] -> wait.  On entry dout[0] and dout[PR-1] hold c'.
+template <int PR, int PC, int NW, int PAR, bool PUBLISH>
+__device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
+                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
+                                         float (&eout)[PR][2]) {
+    using K = Cfg<PR, PC, NW>;
+    const bool ul = !x.first_lane, ur = !x.last_lane;
+    // ---- A: own-row taps of the two boundary rows ----------------------------------------------------------------
+    scatter_row2<PC, 0, true>(w[0], Row<PC>{din[0], ein[0]}, dout[0], ul, ur);
+    scatter_row2<PC, +1, true>(w[0], Row<PC>{din[1], ein[1]}, dout[0], ul, ur);
+    scatter_row2<PC, 0, true>(w[PR - 1], Row<PC>{din[PR - 1], ein[PR - 1]}, dout[PR - 1], ul, ur);
+    scatter_row2<PC, -1, true>(w[PR - 1], Row<PC>{din[PR - 2], ein[PR - 2]}, dout[PR - 1], ul, ur);
+    // ---- B: the neighbours' rows, then publish at once ---------------------------------------------------------------
+#ifndef CSPN_ABLATE_NO_SYNC
+    CSPN_STAMP(x, 5 + 3 * x.step);
+    mbar_wait_dep(x.bar_full0 + 8 * PAR, phase, wait_token<PC>(x, dout[0], dout[PR - 1]));
+    CSPN_STAMP(x, 6 + 3 * x.step);
+#endif
+    {
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
+        const float* pu = p + (2 * wy) * K::TWX;          // row above my patch
+        const float* pd = p + (2 * wy + 3) * K::TWX;      // row below my patch
+        float u[PC], ue[2], d[PC], de[2];
+        load_row_smem(pu, u);
+        load_row_smem(pd, d);
+        ue[0] = pu[-1]; ue[1] = pu[PC];                   // pad floats are zero at the tile edges
+        de[0] = pd[-1]; de[1] = pd[PC];
+        scatter_row2<PC, -1, false>(w[0], Row<PC>{u, ue}, dout[0], true, true);
+        scatter_row2<PC, +1, false>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1], true, true);
+    }
+    if constexpr (PUBLISH) {
+#ifndef CSPN_ABLATE_NO_SYNC
+        publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+        CSPN_STAMP(x, 7 + 3 * x.step);
+#else
+        asm volatile("" ::: "memory");
+#endif
+        row_edges_raw<PC>(dout[0], eout[0]);
+        row_edges_raw<PC>(dout[PR - 1], eout[PR - 1]);
+    }
+    // ---- C: interior rows (their seed is loaded after the publish: see above) ---------------------------------------------
+#ifdef CSPN_SRC_MAJOR
+    // source-major over ALL interior destination rows: the up to 8 FMAs that read one source value are adjacent, so the
+    // value can sit in the operand-reuse cache for all of them (register-file bandwidth is what limits this FMA stream)
+#pragma unroll
+    for (int r = 1; r + 1 < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
+#pragma unroll
+    for (int sr = 0; sr < PR; ++sr) {
+        const Row<PC> src{din[sr], ein[sr]};
+#pragma unroll
+        for (int jx = 0; jx <= PC + 1; ++jx) {
+            const int sx = jx <= PC - 1 ? jx : (jx == PC ? -1 : PC);
+            const float xv = src(sx);
+            if (sr - 1 >= 1 && sr - 1 + 1 < PR) taps_of_source<PC, +1>(w[sr - 1], sx, xv, dout[sr - 1], ul, ur);
+            if (sr >= 1 && sr + 1 < PR) taps_of_source<PC, 0>(w[sr], sx, xv, dout[sr], ul, ur);
+            if (sr + 1 >= 1 && sr + 2 < PR) taps_of_source<PC, -1>(w[sr + 1], sx, xv, dout[sr + 1], ul, ur);
+        }
+        if constexpr (PUBLISH) { if (sr >= 2 && sr - 1 + 1 < PR) row_edges_raw<PC>(dout[sr - 1], eout[sr - 1]); }   // row sr-1 is final
+    }
+#else
+#pragma unroll
+    for (int r = 1; r + 1 < PR; ++r) {
+        load_row_smem(x.cbuf + r * K::TW, dout[r]);
+        scatter_row2<PC, -1, true>(w[r], Row<PC>{din[r - 1], ein[r - 1]}, dout[r], ul, ur);
+        scatter_row2<PC, 0, true>(w[r], Row<PC>{din[r], ein[r]}, dout[r], ul, ur);
+        scatter_row2<PC, +1, true>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r], ul, ur);
+        if constexpr (PUBLISH) row_edges_raw<PC>(dout[r], eout[r]);
+    }
+#endif
+    if constexpr (PUBLISH) {   // seeds of the next step's boundary rows, into the now dead input set
+        load_row_smem(x.cbuf, din[0]);
+        load_row_smem(x.cbuf + (PR - 1) * K::TW, din[PR - 1]);
+    }
+}
+
+#ifndef CSPN_STEP
+#define CSPN_STEP 1
+#endif
+template <int PR, int PC, int NW, int PAR, bool PUBLISH>
+__device__ __forceinline__ void step_fwd(Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
+                                         float (&din)[PR][PC], float (&ein)[PR][2], float (&dout)[PR][PC],
+                                         float (&eout)[PR][2]) {
+#if CSPN_STEP == 3
+    iterate3<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
+#elif CSPN_STEP == 2
+    iterate2<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
+#else
+    iterate<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
+#endif
+#ifdef CSPN_TRACE
+    ++x.step;
+#endif
 }
 
 // What a launch computes with the folded weights w' it builds in its prologue:
@@ -395,10 +640,10 @@ __device__ __forceinline__ void iterate_adj(const Xch& x, int wy, uint32_t phase
     for (int r = 0; r < PR; ++r) fold_edges<PC>(lout[r], xl[r], xr[r], x.first_lane, x.last_lane);
     mbar_wait(x.bar_full0 + 8 * PAR, phase);
     {
-        const float* p = x.base + (size_t)PAR * K::kSlots * K::TW;
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
         float a[PC], b[PC];
-        load_row_smem(p + (2 * wy) * K::TW, a);        // what the warp above owes my top row
-        load_row_smem(p + (2 * wy + 3) * K::TW, b);    // what the warp below owes my bottom row
+        load_row_smem(p + (2 * wy) * K::TWX, a);        // what the warp above owes my top row
+        load_row_smem(p + (2 * wy + 3) * K::TWX, b);    // what the warp below owes my bottom row
 #pragma unroll
         for (int j = 0; j < PC; ++j) { lout[0][j] += a[j]; lout[PR - 1][j] += b[j]; }
     }
@@ -410,7 +655,7 @@ template <int PR, int PC, int NW, bool ABS, bool GENERAL, int MODE = kForward>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
     using K = Cfg<PR, PC, NW>;
-    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP;
+    constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP, TWX = K::TWX;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
@@ -427,11 +672,15 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     const size_t HW = (size_t)H * W;
 
     Xch xc;
-    xc.base = xch + lane * PC;
+#ifdef CSPN_TRACE
+    xc.tr = nullptr;
+    xc.step = 0;
+#endif
+    xc.base = xch + 4 + lane * PC;     // 4 zero floats lead every exchange row
     xc.bar_full0 = bar_full0;
     xc.has_up = crank > 0;
     xc.has_dn = crank + 1 < csize;
-    xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TW), crank - 1) : 0u;
+    xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TWX), crank - 1) : 0u;
     xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
     xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
     xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
@@ -443,6 +692,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
+    xc.zero = (uint32_t)prm.zero;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -473,14 +723,19 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     }
     // every CTA's barriers must be initialised before a neighbour's st.async can target them
     cluster_arrive();
-    // halo slots without a neighbour stay zero for the whole kernel (rows outside the image)
+    // halo slots without a neighbour stay zero for the whole kernel (rows outside the image), and so do the 4 pad
+    // floats on either side of every row (columns outside the tile).  Nobody else ever writes these locations.
     if (!xc.has_up)
-        for (int i = tid; i < TW; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TW + i] = 0.f; }
+        for (int i = tid; i < TWX; i += K::kThreads) { xch[i] = 0.f; xch[(size_t)K::kSlots * TWX + i] = 0.f; }
     if (!xc.has_dn)
-        for (int i = tid; i < TW; i += K::kThreads) {
-            xch[(size_t)(K::kSlots - 1) * TW + i] = 0.f;
-            xch[(size_t)(2 * K::kSlots - 1) * TW + i] = 0.f;
+        for (int i = tid; i < TWX; i += K::kThreads) {
+            xch[(size_t)(K::kSlots - 1) * TWX + i] = 0.f;
+            xch[(size_t)(2 * K::kSlots - 1) * TWX + i] = 0.f;
         }
+    for (int i = tid; i < 2 * K::kSlots * 8; i += K::kThreads) {
+        const int row = i >> 3, c = i & 7;
+        xch[(size_t)row * TWX + (c < 4 ? c : TW + c)] = 0.f;
+    }
     cluster_wait();
 
     uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
@@ -494,6 +749,15 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const float* init = GENERAL ? prm.init : nullptr;
         const int tile_x0 = prm.tile_x0[strip];
         const int x_thr = tile_x0 + lane * PC;  // first column of this thread
+#ifdef CSPN_TRACE
+        {
+            const int slot = (task - (int)cluster_id_x()) / task_stride - 1;    // the cluster's 2nd, 3rd, ... task
+            xc.tr = (prm.trace && cluster_id_x() == 0 && lane == 0 && slot >= 0 && slot < kTraceTasks)
+                        ? prm.trace + ((size_t)(slot * 16 + (int)crank) * 8 + wy) * kTraceEvents : nullptr;
+            xc.step = 0;
+        }
+        CSPN_STAMP(xc, 0);
+#endif
 
         // ---- thread state ---------------------------------------------------------------------------
         float w[PR][PC][8], d[PR][PC];
@@ -531,6 +795,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
         mbar_wait(bar_tma, ph_tma);
         ph_tma ^= 1;
+        CSPN_STAMP(xc, 1);
 
         // ---- prologue: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ------------------
         // a_k(y,x) = g_k(y+dy_k, x+dx_k): dy_k came with the TMA box, dx_k is applied here: the thread reads its own
@@ -571,6 +836,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 }
             }
             float cj[PC];
+            bool exact_div = false;
 #pragma unroll
             for (int j = 0; j < PC; ++j) {
                 const bool in = col_in && (y < H);
@@ -581,6 +847,23 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #pragma unroll
                 for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
                 cj[j] = in ? kappa * d[r][j] : 0.f;
+                // a * (1/S) is a / S to 2 ulp and has the same 0/0, x/inf and inf/inf results, EXCEPT when 1/S overflows
+                // (S subnormal): there the reference's quotient (cspn.py:138) is an ordinary number
+                exact_div |= in && (inv > 8.0e37f);
+            }
+            if (exact_div) {                                   // cold: IEEE division, the reference's own expression
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    const float om = 1.f - m[r][j];
+                    float gsum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float q = __fdiv_rn(a[k][j], S[j]);
+                        gsum += q;                             // gate_sum, cspn.py:139
+                        w[r][j][k] = om * q;
+                    }
+                    cj[j] = (om * (1.f - gsum) + m[r][j]) * d[r][j];
+                }
             }
             // only this thread ever reads these values back: no barrier needed
             if constexpr (MODE != kAdjoint) store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
@@ -590,7 +873,9 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
             }
         }
+        CSPN_STAMP(xc, 2);
         __syncthreads();  // every warp is done with the staging buffer
+        CSPN_STAMP(xc, 3);
 
         // ---- next task's guidance starts streaming in now; it lands while this task iterates in registers ----
         const int next = task + task_stride;
@@ -625,6 +910,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
         }
         first = false;
+        CSPN_STAMP(xc, 4);
         const int iters = prm.iters;
         // kStoreSteps / kAdjoint: every step's result also goes to global memory (useful pixels only); the pass's last
         // step leaves through the epilogue
@@ -672,29 +958,36 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #endif
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
-        for (int r = 0; r < PR; ++r) row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
+        for (int r = 0; r < PR; ++r) {
+#if CSPN_STEP >= 2
+            row_edges_raw<PC>(d[r], e[r]);
+#else
+            row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
+#endif
+        }
         float d2[PR][PC], e2[PR][2];    // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(xc.cbuf + r * TW, d2[r]);   // accumulators of the first step start from c'
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
-            iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            step_fwd<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d2);
-            iterate<PR, PC, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
+            step_fwd<PR, PC, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d);
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
-            iterate<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            step_fwd<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d2);
-            iterate<PR, PC, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
+            step_fwd<PR, PC, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
             ph1 ^= 1;
         } else if (iters - it == 1) {
-            iterate<PR, PC, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
+            step_fwd<PR, PC, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
             ph0 ^= 1;
         }
+        CSPN_STAMP(xc, kTraceEvents - 2);
         cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers (paired with the wait above / after the loop)
         if (iters & 1) {
 #pragma unroll
@@ -719,6 +1012,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 }
             }
         }
+        CSPN_STAMP(xc, kTraceEvents - 1);
     }
     // No CTA may exit while a neighbour could still address its shared memory.
     if (!first) cluster_wait();
@@ -780,6 +1074,7 @@ struct Plan {
 };
 
 std::mutex g_mu;
+unsigned long long* g_trace = nullptr;   // -DCSPN_TRACE builds: set through cspn_debug_set_trace
 struct OccKey { int cfg, cs, dev; };
 std::vector<std::pair<OccKey, int>> g_occ_cache;
 bool g_attr_set[16][16] = {};
@@ -956,6 +1251,13 @@ int get_encode() {
 
 }  // namespace
 
+#ifdef CSPN_TRACE
+// developer hook of the tracing build only (not declared in include/cspn_b200.h): device buffer of
+// kTraceTasks*16*8*kTraceEvents 64-bit stamps, or null to stop tracing
+extern "C" __attribute__((visibility("default"))) void cspn_debug_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
+extern "C" __attribute__((visibility("default"))) int cspn_debug_trace_events() { return kTraceEvents; }
+#endif
+
 bool cluster2d_supported(const Problem2D& p, char* why, int why_len) {
     if (p.iters <= 0) { snprintf(why, why_len, "iters == 0"); return false; }
     if ((reinterpret_cast<uintptr_t>(p.guidance) | reinterpret_cast<uintptr_t>(p.blur) | reinterpret_cast<uintptr_t>(p.sparse) |
@@ -1078,6 +1380,8 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = pp.iters; prm.norm_abs = p.norm_abs;
     prm.n_strips = pp.n_strips;
     prm.n_bands = pp.n_bands;
+    prm.zero = 0;
+    prm.trace = g_trace;
     const long tasks = (long)p.B * p.C * pp.n_strips * pp.n_bands;
     if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
     prm.n_tasks = (int)tasks;
