@@ -94,6 +94,48 @@ def build(force=False, verbose=False, defines=(), out=None):
     return lib
 
 
+TORCH_LIB = os.path.join(OUT_DIR, 'libcspn_b200_torch.so')
+TORCH_STAMP = os.path.join(OUT_DIR, 'torch_op.sha256')
+
+
+def _torch_digest():
+    import torch
+    h = hashlib.sha256()
+    for f in (os.path.join(CSRC, 'torch_op.cpp'), os.path.join(os.path.dirname(HERE), 'include', 'cspn_b200.h')):
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    h.update(torch.__version__.encode())
+    return h.hexdigest()
+
+
+def build_torch_op(force=False):
+    """Compiles csrc/torch_op.cpp (TORCH_LIBRARY registration, a shim over the C ABI) with the host compiler against
+    this interpreter's torch headers and links it to libcspn_b200.so (found at run time through $ORIGIN).
+    Output: cspn_b200/_build/libcspn_b200_torch.so, loaded with torch.ops.load_library by cspn_b200/torch_op.py."""
+    build()
+    if (not force and os.path.isfile(TORCH_LIB) and os.path.isfile(TORCH_STAMP)
+            and open(TORCH_STAMP).read().strip() == _torch_digest()):   # dynamic link: a rebuilt libcspn_b200.so needs no relink
+        return TORCH_LIB
+    import torch
+    from torch.utils import cpp_extension as ce
+    cxx = '/usr/bin/g++' if os.path.isfile('/usr/bin/g++') else (shutil.which('g++') or 'g++')
+    cuda_home = os.environ.get('CUDA_HOME') or '/usr/local/cuda'
+    torch_lib = ce.library_paths()[0]
+    cmd = [cxx, '-O2', '-std=c++17', '-fPIC', '-shared', '-fvisibility=hidden',
+           f'-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}',
+           os.path.join(CSRC, 'torch_op.cpp'), '-o', TORCH_LIB]
+    cmd += [f'-I{d}' for d in ce.include_paths()] + [f'-I{os.path.join(cuda_home, "include")}']
+    cmd += [f'-L{torch_lib}', '-lc10', '-lc10_cuda', '-ltorch_cpu', '-ltorch', f'-L{OUT_DIR}', '-lcspn_b200',
+            '-Wl,-rpath,$ORIGIN', f'-Wl,-rpath,{torch_lib}', '-Wl,--no-as-needed']
+    env = dict(os.environ)
+    env.pop('CC', None)
+    env.pop('CXX', None)
+    subprocess.check_call(cmd, env=env)
+    with open(TORCH_STAMP, 'w') as fh:
+        fh.write(_torch_digest())
+    return TORCH_LIB
+
+
 if __name__ == '__main__':
     import argparse
     ap = argparse.ArgumentParser(description=__doc__)
@@ -101,5 +143,8 @@ if __name__ == '__main__':
     ap.add_argument('-v', dest='verbose', action='store_true')
     ap.add_argument('--define', action='append', default=[], help='extra -D for an experimental variant (repeatable)')
     ap.add_argument('--out', help='output .so of the variant (use with CSPN_B200_LIB)')
+    ap.add_argument('--torch-op', action='store_true', help='also build the TORCH_LIBRARY shim (libcspn_b200_torch.so)')
     a = ap.parse_args()
     print(build(force=a.force, verbose=a.verbose, defines=tuple(a.define), out=a.out))
+    if a.torch_op:
+        print(build_torch_op(force=a.force))

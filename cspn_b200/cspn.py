@@ -10,7 +10,9 @@ device memory, the current stream and autograd plumbing.  There is no CPU / eage
 import torch
 import torch.nn as nn
 
-from . import _lib
+import os
+
+from . import _lib, torch_op
 from ._lib import ALGO_AUTO, ALGO_CLUSTER, ALGO_GENERIC, NORM2D, NORM3D  # noqa: F401
 
 
@@ -41,11 +43,21 @@ def _check_inputs_2d(guidance, blur_depth, sparse_depth):
             raise RuntimeError('sparse_depth must be fp32 on the device of blur_depth')
 
 
-def _check_out(out, like):
+def _overlaps(a, b):
+    """True when the storage ranges of two tensors intersect (same device)."""
+    if a is None or b is None or a.device != b.device or a.numel() == 0 or b.numel() == 0:
+        return False
+    a0, b0 = a.data_ptr(), b.data_ptr()
+    span = lambda t: (sum((n - 1) * abs(st) for n, st in zip(t.shape, t.stride())) + 1) * t.element_size()
+    return a0 < b0 + span(b) and b0 < a0 + span(a)
+
+
+def _check_out(out, like, *inputs):
     if out.shape != like.shape or out.dtype != like.dtype or out.device != like.device or not out.is_contiguous():
         raise ValueError('`out` must be a contiguous tensor with the shape, dtype and device of blur_depth')
-    if out.data_ptr() == like.data_ptr():
-        raise ValueError('`out` must not alias blur_depth')
+    for t in (like,) + inputs:       # include/cspn_b200.h: `out` must not alias the inputs
+        if _overlaps(out, t):
+            raise ValueError('`out` must not alias an input tensor')
 
 
 def propagate2d(guidance, blur_depth, sparse_depth=None, prop_time=24, norm_type='8sum', algo=ALGO_AUTO, out=None):
@@ -56,7 +68,11 @@ def propagate2d(guidance, blur_depth, sparse_depth=None, prop_time=24, norm_type
     blur_depth, contiguous (serving loops reuse one pinned buffer: allocating 55 MB of pinned memory costs milliseconds)."""
     _check_inputs_2d(guidance, blur_depth, sparse_depth)
     if prop_time == 0:
-        return blur_depth                      # cspn.py:61,83 returns the input tensor itself
+        if out is None:
+            return blur_depth                  # cspn.py:61,83 returns the input tensor itself
+        _check_out(out, blur_depth, guidance, sparse_depth)
+        out.copy_(blur_depth)                  # a caller-provided result buffer always holds the result
+        return out
     L = _lib.lib()
     B, C, H, W = blur_depth.shape
     g = guidance.contiguous()
@@ -67,14 +83,14 @@ def propagate2d(guidance, blur_depth, sparse_depth=None, prop_time=24, norm_type
             raise _lib.CspnError('cspn_b200 needs a CUDA device (no CPU implementation exists in this package)')
         if out is None:
             out = torch.empty_like(d, pin_memory=d.is_pinned())  # pinned in -> pinned out: the D2H stays asynchronous
-        _check_out(out, d)
+        _check_out(out, d, g, s)
         rc = L.cspn2d_fwd_f32_host(_ptr(g), _ptr(d), _ptr(s), _ptr(out), B, C, H, W, g.shape[1], int(prop_time),
                                    NORM2D[norm_type], algo, torch.cuda.current_device())
         _lib.check(rc, 'cspn2d_fwd_f32_host')
         return out
     if out is None:
         out = torch.empty_like(d)
-    _check_out(out, d)
+    _check_out(out, d, g, s)
     if algo == ALGO_AUTO and any(t is not None and t.data_ptr() % 16 for t in (g, d, s, out)):
         algo = ALGO_GENERIC   # views at odd storage offsets: the cluster kernel's TMA / float4 accesses need 16-byte bases
     with torch.cuda.device(d.device):
@@ -96,6 +112,7 @@ class _Propagate2dFn(torch.autograd.Function):
         return propagate2d(guidance, blur_depth, sparse_depth, prop_time, norm_type, algo)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         guidance, blur_depth, sparse_depth = ctx.saved_tensors
         prop_time, norm_type = ctx.cfg
@@ -119,6 +136,14 @@ class _Propagate2dFn(torch.autograd.Function):
         return gg, gd, None, None, None, None
 
 
+def _use_torch_op():
+    """The dispatcher-op route is taken when libcspn_b200_torch.so exists (CSPN_B200_NO_TORCH_OP=1 forces ctypes)."""
+    if os.environ.get('CSPN_B200_NO_TORCH_OP') == '1' or not torch_op.available():
+        return False
+    torch_op.load()
+    return True
+
+
 class Affinity_Propagate(nn.Module):
     """Same surface as the reference class (cspn.py:14-39): no parameters, no buffers."""
 
@@ -132,8 +157,15 @@ class Affinity_Propagate(nn.Module):
         self.in_feature = 1
         self.out_feature = 1
         self.algo = algo
+        # torch.ops.cspn_b200.propagate2d (csrc/torch_op.cpp) when the shim is built: one dispatcher op with fake kernel
+        # and autograd formula, so torch.compile / export trace through the module.  Same C ABI underneath; without the
+        # shim the ctypes binding below is used (still the CUDA kernels -- there is no non-native path).
+        self._use_op = _use_torch_op()
 
     def forward(self, guidance, blur_depth, sparse_depth=None):
+        if self._use_op and blur_depth.is_cuda and self.prop_time > 0:
+            sd = None if sparse_depth is None else sparse_depth.detach()   # train.py never differentiates it (:351 clones the input)
+            return torch.ops.cspn_b200.propagate2d(guidance, blur_depth, sd, self.prop_time, NORM2D[self.norm_type], self.algo)
         needs_grad = torch.is_grad_enabled() and (guidance.requires_grad or blur_depth.requires_grad)
         if needs_grad and self.prop_time > 0:
             sd = None if sparse_depth is None else sparse_depth.detach()
@@ -187,6 +219,7 @@ class _Propagate3dFn(torch.autograd.Function):
         return propagate3d(guidance, feat, prop_time, norm_type)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         guidance, feat = ctx.saved_tensors
         prop_time, norm_type = ctx.cfg
@@ -218,8 +251,11 @@ class Affinity_Propagate3D(nn.Module):
         assert prop_kernel == 3, 'only the 3x3x3 (26-neighbour) kernel is supported'      # demo.py:91 choices=[3]
         assert norm_type in NORM3D
         self.prop_time, self.prop_kernel, self.norm_type = prop_time, prop_kernel, norm_type
+        self._use_op = _use_torch_op()
 
     def forward(self, guidance, feat):
+        if self._use_op and feat.is_cuda and self.prop_time > 0:
+            return torch.ops.cspn_b200.propagate3d(guidance, feat, self.prop_time, NORM3D[self.norm_type])
         if torch.is_grad_enabled() and (guidance.requires_grad or feat.requires_grad) and self.prop_time > 0:
             return _Propagate3dFn.apply(guidance, feat, self.prop_time, self.norm_type)
         return propagate3d(guidance, feat, self.prop_time, self.norm_type)

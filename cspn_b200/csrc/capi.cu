@@ -109,6 +109,17 @@ int cspn2d_fwd_f32(const float* guidance, const float* blur, const float* sparse
     if (chosen < 0) { set_error("cluster kernel unsupported for this problem: %s", why); return chosen; }
     g_last_algo = chosen;
     int launches = 0;
+    if (chosen == CSPN_ALGO_GENERIC && algo == CSPN_ALGO_AUTO && iters > 0) {
+        // AUTO sized its workspace for the cluster kernel (cspn2d_workspace_bytes cannot see the pointers); when the
+        // problem then has to take the generic path, say so instead of a bare "workspace too small"
+        const size_t need = generic2d_workspace_bytes(B, C, H, W, iters);
+        if (!workspace || workspace_bytes < need) {
+            set_error("CSPN_ALGO_AUTO falls back to the generic path here (%s), which needs %zu workspace bytes (got %zu): "
+                      "query cspn2d_workspace_bytes(..., CSPN_ALGO_GENERIC) or pass 16-byte aligned tensors",
+                      why[0] ? why : "cluster kernel declined", need, workspace ? workspace_bytes : (size_t)0);
+            return CSPN_ERR_WORKSPACE;
+        }
+    }
     rc = (chosen == CSPN_ALGO_CLUSTER) ? cluster2d_forward(p, workspace, workspace_bytes, (cudaStream_t)stream, &launches)
                                        : generic2d_forward(p, workspace, workspace_bytes, (cudaStream_t)stream, &launches);
     g_last_launches = launches;
@@ -236,6 +247,21 @@ int ensure_slot(Slot& s, size_t bytes) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// A host-buffer call that fails half way must not return while earlier chunks' copies and kernels still read the
+// caller's buffers or write the pipeline's: on every exit path that did not reach the final synchronisation, drain.
+struct DrainOnExit {
+    HostPipe& pipe;
+    bool armed = true;
+    explicit DrainOnExit(HostPipe& p) : pipe(p) {}
+    ~DrainOnExit() {
+        if (!armed) return;
+        for (auto& s : pipe.slots)
+            if (s.stream) cudaStreamSynchronize(s.stream);
+        if (pipe.result.stream) cudaStreamSynchronize(pipe.result.stream);
+        cudaGetLastError();    // the status the caller sees is the one already recorded
+    }
+};
+
 }  // namespace
 }  // namespace cspn
 
@@ -251,6 +277,7 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
     if (!guard.ok) { set_error("cannot select device %d", device); return CSPN_ERR_CUDA; }
     HostPipe& pipe = g_pipes[device];
     std::lock_guard<std::mutex> lock(pipe.mu);
+    DrainOnExit drain(pipe);
 
     const size_t HW = (size_t)H * W;
     // chunk: about 48 MB of input per slot keeps PCIe transfers long and the kernel grid full
@@ -315,6 +342,7 @@ extern "C" CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* 
         }
     CSPN_CUDA_TRY(cudaMemcpyAsync(out, dout_all, (size_t)B * C * HW * sizeof(float), cudaMemcpyDeviceToHost, pipe.result.stream));
     CSPN_CUDA_TRY(cudaStreamSynchronize(pipe.result.stream));
+    drain.armed = false;
     g_last_launches = launches;
     return CSPN_OK;
 }
@@ -332,6 +360,7 @@ extern "C" CSPN_API int cspn3d_fwd_f32_host(const float* guidance, const float* 
     if (!guard.ok) { set_error("cannot select device %d", device); return CSPN_ERR_CUDA; }
     HostPipe& pipe = g_pipes[device];
     std::lock_guard<std::mutex> lock(pipe.mu);
+    DrainOnExit drain(pipe);
     const size_t V = (size_t)D * H * W;
     const size_t g_bytes = align_up(26 * V * sizeof(float), 256);
     const size_t f_bytes = align_up((size_t)C * V * sizeof(float), 256);
@@ -355,6 +384,7 @@ extern "C" CSPN_API int cspn3d_fwd_f32_host(const float* guidance, const float* 
     }
     for (auto& s : pipe.slots)
         if (s.stream) CSPN_CUDA_TRY(cudaStreamSynchronize(s.stream));
+    drain.armed = false;
     g_last_launches = launches;
     return CSPN_OK;
 }

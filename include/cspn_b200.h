@@ -76,6 +76,10 @@ typedef enum {
  * out      [B][C][H][W]   must not alias the inputs
  * iters    prop_time >= 0 (0 copies blur to out, cspn.py:61,83)
  */
+/* Workspace for `algo`.  CSPN_ALGO_AUTO assumes what the cluster kernel needs of its tensors -- W % 4 == 0 and 16-byte
+ * aligned base pointers (every allocator's default) -- because the query cannot see the pointers; if a call then has to
+ * take the generic path (misaligned views), cspn2d_fwd_f32 returns CSPN_ERR_WORKSPACE with a message naming
+ * cspn2d_workspace_bytes(..., CSPN_ALGO_GENERIC) as the size to provide. */
 CSPN_API size_t cspn2d_workspace_bytes(int B, int C, int H, int W, int iters, int algo);
 
 CSPN_API int cspn2d_fwd_f32(const float* guidance, const float* blur, const float* sparse, float* out,
