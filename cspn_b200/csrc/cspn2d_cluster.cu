@@ -166,7 +166,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
 //   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
 //   then cbuf[RB][TW]         folded constant term c' of the current task
-//   then 3 mbarriers          tma, full[0], full[1]
+//   then mbarriers            tma, full[group 0][parity 0,1], full[group 1][parity 0,1]
 //
 // Arithmetic is scalar FFMA on purpose.  fma.rn.f32x2 (FFMA2, new on sm_100) was tried with pixel pairs in 64-bit
 // registers: with 160 weight registers live per thread it sustains only ~0.22 FFMA2/clk per sub-partition (715 cycles
@@ -180,6 +180,16 @@ struct Cfg {
     static constexpr int TW = 32 * PC;   // tile (strip) width
     static constexpr int TWP = TW + 8;   // staged row pitch: 4 apron columns on each side
     static constexpr int kSlots = 2 * NW + 2;
+    // Warp groups (-DCSPN_GROUPS=2): the upper and the lower half of the CTA's warps synchronise on their own mbarrier
+    // pair and run about half a step apart.  Warps w and w + NW/2 share an SM sub-partition, so while one of them sits
+    // in the latency-bound part of its step (barrier wait -> halo rows -> publish) the other one is in its FMA-bound part:
+    // with one CTA-wide barrier all warps reach that bubble together and the sub-partition idles (~170 cycles per step,
+    // profiles/r02_trace_*.txt).
+#ifndef CSPN_GROUPS
+#define CSPN_GROUPS 1
+#endif
+    static constexpr int kGroups = (CSPN_GROUPS == 2 && NW >= 4) ? 2 : 1;
+    static constexpr int kGroupWarps = NW / kGroups;
     // exchange rows carry 4 zero floats on each side: a thread reads the x-neighbours of a halo row straight from the
     // row (lane 0 / 31 find the zeros), so the halo taps need neither shuffles nor selects
     static constexpr int TWX = TW + 8;
@@ -287,6 +297,8 @@ struct Xch {
     // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
     // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
     bool remote_up, remote_dn, sig_tx, sig;
+    uint32_t cross_bar;   // two warp groups: full[0] of the OTHER group, for the warp whose row that group reads
+    bool cross;
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
     uint32_t zero;        // 0 at run time, opaque at compile time
@@ -323,6 +335,7 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     __syncwarp();
     mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
     mbar_arrive_if(bar, x.sig);
+    if constexpr (K::kGroups == 2) mbar_arrive_if(x.cross_bar + 8 * PAR, x.cross);   // my row is read by the other group
 }
 
 // One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
@@ -677,18 +690,28 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.step = 0;
 #endif
     xc.base = xch + 4 + lane * PC;     // 4 zero floats lead every exchange row
-    xc.bar_full0 = bar_full0;
+    // barrier of group g, parity p: bar_full0 + 16 g + 8 p.  One group: everything on group 0.
+    constexpr int kGroups = K::kGroups, kGroupWarps = K::kGroupWarps;
+    const int group = wy / kGroupWarps;
+    const uint32_t bar_last_group = bar_full0 + 16 * (kGroups - 1);     // the group that owns the CTA's bottom rows
+    xc.bar_full0 = bar_full0 + 16 * group;
     xc.has_up = crank > 0;
     xc.has_dn = crank + 1 < csize;
+    // my top row is read by the LAST group of the CTA above, my bottom row by the FIRST group of the CTA below
     xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TWX), crank - 1) : 0u;
-    xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
+    xc.up_bar = xc.has_up ? map_to_cta(bar_last_group, crank - 1) : 0u;
     xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
     xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
-    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
+    // halo bytes my group's barrier receives per exchange, and the warp that arms them (the one that reads the halo)
+    const bool rx_up = xc.has_up && group == 0, rx_dn = xc.has_dn && group == kGroups - 1;
+    xc.rx_bytes = (uint32_t)((rx_up ? 1 : 0) + (rx_dn ? 1 : 0)) * TW * sizeof(float);
+    const bool armer = kGroups == 1 ? wy == 0 : (wy == 0 || wy == NW - 1);
     xc.remote_up = xc.has_up && wy == 0;
     xc.remote_dn = xc.has_dn && wy == NW - 1;
-    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
-    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
+    xc.sig_tx = lane == 0 && armer && xc.rx_bytes != 0;
+    xc.sig = lane == 0 && !(armer && xc.rx_bytes != 0);
+    xc.cross = kGroups == 2 && lane == 0 && (wy == kGroupWarps - 1 || wy == kGroupWarps);
+    xc.cross_bar = bar_full0 + 16 * (1 - group);
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
@@ -715,8 +738,10 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        mbar_init(bar_full0, NW);
-        mbar_init(bar_full0 + 8, NW);
+        for (int g = 0; g < K::kGroups; ++g) {     // a group's warps + (two groups) the adjacent warp of the other group
+            mbar_init(bar_full0 + 16 * g, K::kGroupWarps + (K::kGroups - 1));
+            mbar_init(bar_full0 + 16 * g + 8, K::kGroupWarps + (K::kGroups - 1));
+        }
         fence_barrier_init();
         fence_proxy_async();
         if (task < n_tasks) issue_stage(task);
@@ -764,6 +789,134 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const float* blur = prm.blur + (size_t)bc * HW;
         const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
 
+#ifndef CSPN_PROLOGUE
+#define CSPN_PROLOGUE 2
+#endif
+#if CSPN_PROLOGUE == 2
+        // ---- prologue, pipelined: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ---------------------------
+        // blur / sparse rows are REQUESTED first (straight from global: aligned, read once, prefetched into L2 by the
+        // previous task; W % 4 == 0 and x_thr % 4 == 0, so a float4 is entirely inside or outside the image) and CONSUMED
+        // kLag rows later: phase 1 of a row (gather the 8 affinities, sum |a|, reciprocal) needs only the staged guidance,
+        // phase 2 (mask folding, c') needs the loaded values.  Their L2 latency hides under phase 1 of the first rows.
+        const bool col_in = (x_thr >= 0) && (x_thr < W);
+        float4 dv[PR], sv[PR];
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+            const int y = y_thr + r;
+            dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sv[r] = dv[r];
+            if (col_in && y < H) {
+                dv[r] = __ldg(reinterpret_cast<const float4*>(blur + (size_t)y * W + x_thr));
+                if (sparse) sv[r] = __ldg(reinterpret_cast<const float4*>(sparse + (size_t)y * W + x_thr));
+            }
+        }
+        // the neighbours have finished reading the exchange buffers of the previous task (they arrived right after their
+        // step loop): waited for here, where its latency overlaps the loads above, not in front of the step loop
+        if (!first) cluster_wait();
+        // the first row exchange of a task needs only blur_depth: it is published from inside the prologue (below), so its
+        // DSMEM round trip hides under the normalisation instead of stalling the first step
+        const bool early_publish = (MODE != kAdjoint) && !(GENERAL && init != nullptr);
+
+        mbar_wait(bar_tma, ph_tma);
+        ph_tma ^= 1;
+        CSPN_STAMP(xc, 1);
+
+        constexpr int kLag = PR >= 3 ? 2 : 1;
+        float inv[PR][PC];
+#pragma unroll
+        for (int s = 0; s < PR + kLag; ++s) {
+            if (s < PR) {
+                // ---- phase 1 of row s: a_k(y,x) = g_k(y+dy_k, x+dx_k).  dy_k came with the TMA box; dx_k is applied here:
+                // the thread reads its own PC columns of plane k and takes the missing neighbour column from the next /
+                // previous lane (tile edge lanes read the apron column of the staged row instead).  w holds the raw a_k.
+                const int r = s;
+                float S[PC];
+#pragma unroll
+                for (int j = 0; j < PC; ++j) S[j] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
+                    float v[PC], a[PC];
+                    load_row_smem(row, v);
+                    if (off2_dx(k) == 1) {
+                        float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
+                        if (lane == 31) nb = row[PC];
+#pragma unroll
+                        for (int j = 0; j < PC - 1; ++j) a[j] = v[j + 1];
+                        a[PC - 1] = nb;
+                    } else if (off2_dx(k) == -1) {
+                        float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
+                        if (lane == 0) nb = row[-1];
+#pragma unroll
+                        for (int j = PC - 1; j > 0; --j) a[j] = v[j - 1];
+                        a[0] = nb;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PC; ++j) a[j] = v[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        if (ABS) a[j] = fabsf(a[j]);             // cspn.py:88-89
+                        S[j] += fabsf(a[j]);                      // cspn.py:135-136
+                        w[r][j][k] = a[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PC; ++j) inv[r][j] = rcp_approx(S[j]);
+            }
+            if (s == kLag && early_publish) {
+                const float top[PC] = {dv[0].x, dv[0].y, dv[0].z, dv[0].w};
+                const float bot[PC] = {dv[PR - 1].x, dv[PR - 1].y, dv[PR - 1].z, dv[PR - 1].w};
+                publish<PR, PC, NW, 0>(xc, wy, top, bot);
+            }
+            if (s >= kLag) {
+                // ---- phase 2 of row s - kLag: w'_k = (1-m) a_k / S, c' = (1 - sum_k w'_k) d_0 -----------------------------
+                const int r = s - kLag;
+                const bool in = col_in && (y_thr + r < H);
+                d[r][0] = dv[r].x; d[r][1] = dv[r].y; d[r][2] = dv[r].z; d[r][3] = dv[r].w;
+                const float mm[PC] = {signf(sv[r].x), signf(sv[r].y), signf(sv[r].z), signf(sv[r].w)};
+                float cj[PC];
+                bool exact_div = false;
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    // a * (1/S) is a / S to 2 ulp and has the same 0/0, x/inf and inf/inf results, EXCEPT when 1/S
+                    // overflows (S subnormal): there the reference's quotient (cspn.py:138) is an ordinary number
+                    exact_div |= in && (inv[r][j] > 8.0e37f);
+                }
+                if (exact_div) {                               // cold: IEEE division, the reference's own expression
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        float S = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) S += fabsf(w[r][j][k]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) w[r][j][k] = __fdiv_rn(w[r][j][k], S);
+                        inv[r][j] = 1.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PC; ++j) {
+                    const float scale = in ? (1.f - mm[j]) * inv[r][j] : 0.f;   // outside the image: w = 0, c = 0, d = 0 forever
+                    float sw = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        w[r][j][k] *= scale;
+                        sw += w[r][j][k];
+                    }
+                    // (1-m)(1 - gate_sum) + m  ==  1 - sum_k w'_k: the sum of the QUOTIENTS as cspn.py:139 forms it (a sum
+                    // of the raw affinities times 1/S would turn an overflowing sum into inf * 0 = NaN)
+                    cj[j] = in ? (1.f - sw) * d[r][j] : 0.f;
+                }
+                // only this thread ever reads these values back: no barrier needed
+                if constexpr (MODE != kAdjoint) store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
+                // a pass after the first continues from the previous pass's result; c' above still used d_0
+                if (GENERAL && init != nullptr && in) {
+                    const float4 iv = __ldg(reinterpret_cast<const float4*>(init + (size_t)bc * HW + (size_t)(y_thr + r) * W + x_thr));
+                    d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
+                }
+            }
+        }
+#else
         // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2).
         // W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
         const bool col_in = (x_thr >= 0) && (x_thr < W);
@@ -778,19 +931,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             }
             d[r][0] = dv.x; d[r][1] = dv.y; d[r][2] = dv.z; d[r][3] = dv.w;
             m[r][0] = signf(sv.x); m[r][1] = signf(sv.y); m[r][2] = signf(sv.z); m[r][3] = signf(sv.w);
-        }
-
-        // Build-time experiment for the next tuning round (-DCSPN_EARLY_PUBLISH, off by default, not yet measured): the
-        // first row exchange of a task only needs blur_depth, so it can be issued before the prologue and its DSMEM
-        // round trip hides under the ~2.5 us of normalisation instead of stalling the first step.
-#ifdef CSPN_EARLY_PUBLISH
-        constexpr bool kEarlyPublish = (MODE == kForward) && !GENERAL;
-#else
-        constexpr bool kEarlyPublish = false;
-#endif
-        if constexpr (kEarlyPublish) {
-            if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
-            publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
         }
 
         mbar_wait(bar_tma, ph_tma);
@@ -843,10 +983,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 const float inv = rcp_approx(S[j]);
                 const float om = 1.f - m[r][j];
                 const float scale = in ? om * inv : 0.f;      // pixels outside the image: w = 0, c = 0, d = 0 forever
-                const float kappa = om * (1.f - A[j] * inv) + m[r][j];
+                float sw = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[r][j][k] = a[k][j] * scale;
-                cj[j] = in ? kappa * d[r][j] : 0.f;
+                for (int k = 0; k < 8; ++k) { w[r][j][k] = a[k][j] * scale; sw += w[r][j][k]; }
+                // (1-m)(1 - gate_sum) + m == 1 - sum_k w'_k, formed from the quotients as cspn.py:139 does
+                cj[j] = in ? (1.f - sw) * d[r][j] : 0.f;
                 // a * (1/S) is a / S to 2 ulp and has the same 0/0, x/inf and inf/inf results, EXCEPT when 1/S overflows
                 // (S subnormal): there the reference's quotient (cspn.py:138) is an ordinary number
                 exact_div |= in && (inv > 8.0e37f);
@@ -873,6 +1014,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
             }
         }
+        const bool early_publish = false;
+#endif
         CSPN_STAMP(xc, 2);
         __syncthreads();  // every warp is done with the staging buffer
         CSPN_STAMP(xc, 3);
@@ -906,11 +1049,22 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         }
 
         // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
-        if constexpr (!kEarlyPublish) {
-            if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
-        }
+#if CSPN_PROLOGUE != 2
+        if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
+#endif
         first = false;
         CSPN_STAMP(xc, 4);
+#ifndef CSPN_SKEW
+#define CSPN_SKEW 300
+#endif
+        if constexpr (K::kGroups == 2) {
+            // start the lower warp group late by about half a step: the two groups then stay out of phase for the whole
+            // task (nothing pulls them back together: each only waits for rows the other one published long before)
+            if (group == 1) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < CSPN_SKEW) {}
+            }
+        }
         const int iters = prm.iters;
         // kStoreSteps / kAdjoint: every step's result also goes to global memory (useful pixels only); the pass's last
         // step leaves through the epilogue
@@ -954,7 +1108,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             cluster_arrive_relaxed();
         } else {
 #ifndef CSPN_ABLATE_NO_SYNC
-        if constexpr (!kEarlyPublish) publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
+        if (!early_publish) publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
 #endif
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
@@ -1360,19 +1514,45 @@ int plan_for_launch(const Problem2D& p, Plan& plan) {
 int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const float* start, const float* init, float* out,
                 float* iter_out, long long iter_stride, cudaStream_t stream) {
     const KernelCfg& k = configs()[pp.cfg];
-    // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane
+    // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane.  The descriptor is a
+    // pure function of (base pointer, shape, box): serving loops call with the same buffers again and again, so the last
+    // few encodings are kept (the driver call costs microseconds, which is what a 1-image problem lasts).
     CUtensorMap tm;
-    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
-    CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H,
-                  p.B * p.gch, k.TW(), k.RB());
-        return CSPN_ERR_CUDA;
+    {
+        struct MapKey { const void* base; int W, H, planes, bx, by; };
+        struct MapEntry { MapKey key; CUtensorMap tm; };
+        static MapEntry cache[8];
+        static int n_cached = 0, next_slot = 0;
+        const MapKey key{p.guidance, p.W, p.H, p.B * p.gch, k.TW() + 8, k.RB()};
+        bool hit = false;
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            for (int i = 0; i < n_cached && !hit; ++i) {
+                const MapKey& c = cache[i].key;
+                if (c.base == key.base && c.W == key.W && c.H == key.H && c.planes == key.planes && c.bx == key.bx && c.by == key.by) {
+                    tm = cache[i].tm;
+                    hit = true;
+                }
+            }
+        }
+        if (!hit) {
+            const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
+            const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
+            CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H,
+                          p.B * p.gch, k.TW(), k.RB());
+                return CSPN_ERR_CUDA;
+            }
+            std::lock_guard<std::mutex> lock(g_mu);
+            cache[next_slot] = MapEntry{key, tm};
+            next_slot = (next_slot + 1) % 8;
+            if (n_cached < 8) ++n_cached;
+        }
     }
     ClusterParams prm;
     prm.blur = start; prm.init = init; prm.sparse = p.sparse; prm.out = out;
