@@ -24,6 +24,14 @@ ALGO_BYTES_PER_PX = 44          # read 8 guidance + blur + spars
 METRIC = 'CSPN Mpixels/s (24-iter 2D, 1216x352)'
 
 
+def workload_config(world):
+    """The SAME dict in both arms (ours and --impl reference): the driver compares them."""
+    return {'workload': f'2D CSPN 3x3, {ITERS} iters, {NORM}, with sparse depth (Bernoulli 500 samples/image), batch '
+                        f'{B_PER_GPU}x{W}x{H} fp32 per GPU (BASELINE configs[1]; N=8 is configs[4])',
+            'global_batch': world * B_PER_GPU,
+            'parallelism': f'dp{world} (independent images per rank, no data-path collective)'}
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -122,44 +130,67 @@ def time_torch_port(nb, steps, warmup, threads):
     return nb * H * W * steps / dt / 1e6, dt / steps
 
 
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def time_torch_port_median(nb, reps, warmup, threads):
+    """Median over `reps` single forwards after `warmup` (warm-up + median)."""
+    import torch
+    from cspn_b200.synth import make_inputs
+    from oracle import cspn_torch_port as tp
+    torch.set_num_threads(threads)
+    g, d, s = make_inputs(0, nb, 1, H, W)
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            tp.cspn2d_torch(g, d, s, ITERS, NORM)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    t = median(ts)
+    return nb * H * W / t / 1e6, t
+
+
 def best_torch_threads():
     """The reference's op sequence is ~700 small ATen ops per forward: oversubscribing a 128-thread host makes it
-    20x slower than a few threads.  'All the host threads it can use' = the count that maximises its throughput."""
+    20x slower than a few threads.  'All the host threads it can use' = the count that maximises its throughput:
+    per candidate one warm-up and the median of 3 single-image forwards."""
     ncpu = os.cpu_count() or 1
     best, best_t = 1, float('inf')
-    for n in sorted({min(ncpu, c) for c in (4, 8, 16, 32, 64, ncpu)}):
-        t = time_torch_port(1, 1, 1 if n == 4 else 0, n)[1]
+    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64)}):
+        t = time_torch_port_median(1, 3, 1, n)[1]
         if t < best_t:
             best, best_t = n, t
     return best, best_t
 
 
 def cpu_baseline_leg():
-    """Bounded sample (about 10-30 s): torch-op port of the reference, plus the C/OpenMP oracle for context."""
+    """Bounded sample (about 20 s): the reference's op sequence at B=4 (BASELINE.md section 3's plan) and at B=1 (the
+    reference's own eval batch, eval.py:39), plus the C/OpenMP oracle and the same ops run eagerly on this GPU for context."""
     import torch
     from cspn_b200.synth import make_inputs
     from oracle import c_oracle
-    threads, t1 = best_torch_threads()
-    nb = max(1, min(8, int(12.0 / max(t1, 1e-3) / 3)))            # ~12 s over 1 warm-up + 2 timed forwards
-    mpx, per = time_torch_port(nb, 2, 1, threads)
-    g, d, s = make_inputs(0, 8, 1, H, W)
+    threads, _ = best_torch_threads()
+    mpx4, t4 = time_torch_port_median(4, 3, 1, threads)
+    mpx1, t1 = time_torch_port_median(1, 5, 2, threads)
+    g, d, s = make_inputs(0, 4, 1, H, W)
     gn, dn, sn = g.numpy(), d.numpy(), s.numpy()
     ncpu = os.cpu_count() or 1
     c_mpx, c_thr = 0.0, 1
-    for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):      # the OpenMP port also has a sweet spot
+    for nt in sorted({min(ncpu, c) for c in (16, 32, 64)}):      # the OpenMP port also has a sweet spot
         c_oracle.cspn2d(gn[:1], dn[:1], sn[:1], ITERS, NORM, nthreads=nt)
         t0 = time.perf_counter()
         c_oracle.cspn2d(gn, dn, sn, ITERS, NORM, nthreads=nt)
-        r = 8 * H * W / (time.perf_counter() - t0) / 1e6
+        r = 4 * H * W / (time.perf_counter() - t0) / 1e6
         if r > c_mpx:
             c_mpx, c_thr = r, nt
-    # for context only: the same reference op sequence run eagerly on this GPU (the reference's native mode:
-    # ~700 library-kernel launches per forward), 4 images
     gpu_eager = None
     try:
         from oracle import cspn_torch_port as tp
         if torch.cuda.is_available():
-            gg, dd, ss = [t[:4].cuda() for t in (g, d, s)]
+            gg, dd, ss = [t.cuda() for t in (g, d, s)]
             with torch.no_grad():
                 tp.cspn2d_torch(gg, dd, ss, ITERS, NORM)
                 torch.cuda.synchronize()
@@ -170,34 +201,41 @@ def cpu_baseline_leg():
             gpu_eager = round(3 * 4 * H * W / (time.perf_counter() - t0) / 1e6, 1)
     except Exception:
         gpu_eager = None
-    return {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'cores': threads, 'kind': 'port',
+    return {'value': round(mpx4, 3), 'unit': 'Mpixels/s', 'cores': threads, 'kind': 'port',
+            'sample': f'4x{W}x{H} images (B=4: BASELINE.md section 3), {ITERS} iters, {NORM}, with sparse depth: 1 warm-up + median of '
+                      f'3 forwards of oracle/cspn_torch_port.py (the reference op sequence of cspn.py:42-83 on CPU; '
+                      f'/root/reference is absent on this box); {threads} torch threads = the fastest of 8/16/32/64 on this host '
+                      f'(warm-up + median of 3 each)',
+            'ms_per_forward': round(t4 * 1e3, 1),
+            'b1_value': round(mpx1, 3), 'b1_ms_per_forward': round(t1 * 1e3, 1),
+            'b1_note': 'batch 1 is the reference eval batch (eval.py:39); its ~700 small ops run several times faster per pixel '
+                       'there than at larger batches',
             'reference_ops_eager_on_this_gpu_mpx_s': gpu_eager,
-            'sample': f'{nb}x{W}x{H} images, {ITERS} iters, 1 warm-up + 2 timed forwards of oracle/cspn_torch_port.py '
-                      f'(the reference op sequence of cspn.py:42-83 on CPU; /root/reference is absent on this box); '
-                      f'{threads} torch threads = the fastest of 4..{os.cpu_count()} on this host',
             'host_cpus': os.cpu_count(),
             'c_openmp_port_mpx_s': round(c_mpx, 3), 'c_openmp_threads': c_thr}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (torch-op port), rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path (torch-op port), rank 0 only.  Each step is a
+    B=4 sample of the workload (Mpx/s is what is compared); K steps after W warm-up steps."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads, _ = best_torch_threads()
+    threads, t1 = best_torch_threads()
     budget = 150.0                                               # seconds for the whole run
-    t_img = time_torch_port(4, 1, 1, threads)[1] / 4             # per-image time at a batch that no longer fits the caches
-    nb = max(1, min(B_PER_GPU, int(budget / ((args.steps + args.warmup) * max(t_img, 1e-3)))))
+    nb = 4
+    while nb > 1 and (args.steps + args.warmup) * nb * t1 * 2.0 > budget:   # larger batches run ~2x slower per image than B=1
+        nb //= 2
     mpx, per = time_torch_port(nb, args.steps, args.warmup, threads)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': round(mpx, 3), 'unit': 'Mpixels/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(per * 1e3, 3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'2D CSPN 3x3, {ITERS} iters, {NORM}, batch {B_PER_GPU}x{W}x{H} per GPU (BASELINE configs[1])',
-                   'sample_batch': nb},
+        'config': workload_config(args.gpus),
         'cpu_baseline': {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'each step = {nb}x{W}x{H} images through oracle/cspn_torch_port.py (reference op '
-                                   f'sequence, cspn.py:42-83) with {threads} torch threads (fastest of 4..{os.cpu_count()})', 'host_cpus': os.cpu_count()},
+                         'sample': f'each step = {nb}x{W}x{H} images of the workload (same shape, iters, norm and sparse depth) through '
+                                   f'oracle/cspn_torch_port.py (reference op sequence, cspn.py:42-83) with {threads} torch threads '
+                                   f'(fastest of 8/16/32/64, warm-up + median of 3 each)', 'host_cpus': os.cpu_count()},
         'e2e': {'value': round(mpx, 3), 'unit': 'Mpixels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -226,6 +264,103 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + '\n').encode())
 
 
+def event_times(fn, reps, warmup, pre=None):
+    """CUDA-event duration (ms) of each of `reps` calls of fn() after `warmup` calls; `pre(i)` runs untimed before call i."""
+    import torch
+    for i in range(warmup):
+        if pre:
+            pre(i)
+        fn()
+    evs = []
+    for i in range(reps):
+        if pre:
+            pre(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return sorted(a.elapsed_time(b) for a, b in evs)
+
+
+def other_configs(dev, peak, sm_max_mhz):
+    """The BASELINE.json configs the headline value is not quoted on: configs[2] (NYU-shape iteration sweep), the 304x228
+    single image of configs[0] (latency) and configs[3] (3D), each timed with CUDA events on this GPU."""
+    import torch
+    import cspn_b200
+    from cspn_b200 import _lib
+    from cspn_b200.synth import make_inputs, make_inputs_3d
+    L = _lib.lib()
+    out = {}
+    fma_peak = 148 * 128 * (sm_max_mhz or 1965) * 1e6          # FMA/s at the maximum SM clock
+    # ---- configs[2]: 64 x 304x228, N in {4,8,16,24,48}; two input sets alternate (2 x 195 MB > 126 MB L2) ----------------
+    Bn, Hn, Wn = 64, 228, 304
+    sets = [[t.to(dev) for t in make_inputs(sd, Bn, 1, Hn, Wn)] for sd in (1, 2)]
+    px = Bn * Hn * Wn
+    sweep = {}
+    for n in (4, 8, 16, 24, 48):
+        state = {'i': 0}
+
+        def call():
+            g, d, s = sets[state['i'] & 1]
+            state['i'] += 1
+            return cspn_b200.propagate2d(g, d, s, n, NORM)
+        ms = event_times(call, 10, 3)
+        t = ms[len(ms) // 2] * 1e-3
+        rate = px / t
+        sweep[str(n)] = {'us': round(t * 1e6, 1), 'mpx_s': round(rate / 1e6, 1),
+                         'hbm_gbs': round(ALGO_BYTES_PER_PX * rate / 1e9, 1), 'hbm_frac': round(ALGO_BYTES_PER_PX * rate / 1e9 / peak, 4),
+                         'fp32_ceiling_mpx_s': round(fma_peak / (8 * n + 30) / 1e6, 1),
+                         'fp32_frac': round(rate / (fma_peak / (8 * n + 30)), 4),
+                         'launches': L.cspn_last_launches(), 'algo': _lib.ALGO_NAMES[L.cspn_last_algo()]}
+    out['cfg3_nyu_sweep'] = {'workload': f'2D CSPN 3x3, {NORM}, with sparse depth, batch {Bn}x{Wn}x{Hn} (BASELINE configs[2])',
+                             'timing': 'median of 10 CUDA-event timed calls after 3 warm-up; two input sets alternate '
+                                       '(2 x 195 MB > 126 MB L2)',
+                             'fp32_ceiling': f'148 SM x 128 FMA/clk x {sm_max_mhz} MHz / (8 N + 30) FMA per pixel (BASELINE.md section 2)',
+                             'by_iters': sweep}
+    del sets
+    # ---- configs[0]'s shape on the GPU: one 304x228 image, latency of the call ------------------------------------------
+    g, d, s = [t.to(dev) for t in make_inputs(0, 1, 1, Hn, Wn)]
+    ms = event_times(lambda: cspn_b200.propagate2d(g, d, s, ITERS, NORM), 50, 5)
+    lat = {'workload': f'2D CSPN 3x3, {ITERS} iters, 1x{Wn}x{Hn} (the shape of BASELINE configs[0])', 'us_median': round(ms[25] * 1e3, 1),
+           'us_min': round(ms[0] * 1e3, 1), 'mpx_s': round(Hn * Wn / (ms[25] * 1e-3) / 1e6, 1), 'note': 'L2-resident (3 MB): a latency figure'}
+    try:
+        from cspn_b200 import torch_op
+        torch_op.load()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            torch.ops.cspn_b200.propagate2d(g, d, s, ITERS, 0, 0)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            torch.ops.cspn_b200.propagate2d(g, d, s, ITERS, 0, 0)
+        ms = event_times(graph.replay, 50, 5)
+        lat['us_cuda_graph_replay'] = round(ms[25] * 1e3, 1)
+    except Exception as e:          # the torch-op shim is optional
+        lat['us_cuda_graph_replay'] = None
+        lat['graph_note'] = str(e)[:120]
+    out['cfg1_shape_latency'] = lat
+    # ---- configs[3]: 3D, 8 x 64x96x312, 12 iters (parity unpinned: the Paddle op's source is not in the reference) --------
+    B3, D3, H3, W3, N3 = 8, 64, 96, 312, 12
+    g3, f3 = [t.to(dev) for t in make_inputs_3d(0, B3, 1, D3, H3, W3)]
+    vox = B3 * D3 * H3 * W3
+    r3 = {}
+    for mode in ('26sum_abs', 'paddle'):
+        ms = event_times(lambda: cspn_b200.propagate3d(g3, f3, N3, mode), 5, 2)
+        t = ms[len(ms) // 2] * 1e-3
+        r3[mode] = {'ms': round(t * 1e3, 3), 'mvox_s': round(vox / t / 1e6, 1), 'hbm_gbs': round(112 * vox / t / 1e9, 1),
+                    'hbm_frac': round(112 * vox / t / 1e9 / peak, 4), 'launches': L.cspn_last_launches()}
+    tr = recorded_traffic('step3d')
+    out['cfg4_3d'] = {'workload': f'3D CSPN 3x3x3, {N3} iters, volume {B3}x{D3}x{H3}x{W3} [B,D,H,W], 26-channel guidance (BASELINE configs[3])',
+                      'unit': 'Mvoxels/s; algorithmic 112 B/voxel (26 guidance + 1 read + 1 write, fp32)', 'parity': 'unpinned (3D arithmetic '
+                      'is not in the reference tree; checked against the repo\'s own restatement)', 'by_norm': r3,
+                      'traffic_per_step_launch_per_volume': tr,
+                      'timing': 'median of 5 CUDA-event timed calls after 2 warm-up; inputs 1.7 GB > L2'}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -234,6 +369,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--algo', default='auto', choices=['auto', 'generic', 'cluster'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -248,6 +384,7 @@ def main():
 
     import cspn_b200
     from cspn_b200 import _lib
+    from cspn_b200.sharding import bind_to_gpu_numa
     from cspn_b200.synth import make_inputs
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -260,6 +397,7 @@ def main():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback exists)')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None      # before any pinned allocation (first touch)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         # keep stdout to the single JSON line: NCCL's version banner / debug log goes to stderr
@@ -305,14 +443,7 @@ def main():
     value = world * px / (ms_per_step * 1e-3) / 1e6
 
     # ---- dominant-kernel roofline: events around each launch sequence of one step, averaged --------
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    for a, b in evs:
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    kern_ms = sorted(a.elapsed_time(b) for a, b in evs)
+    kern_ms = event_times(step, args.steps, 0)
     kern_ms_avg = sum(kern_ms) / len(kern_ms)
     peak, peak_src = measured_hbm_peak()
     achieved = ALGO_BYTES_PER_PX * px / (kern_ms_avg * 1e-3) / 1e9
@@ -339,46 +470,78 @@ def main():
     e2e = {'value': round(world * px / float(e2e_s.item()) / 1e6, 1), 'unit': 'Mpixels/s',
            'h2d_bytes_per_step': world * 10 * px * 4, 'd2h_bytes_per_step': world * px * 4,
            'ms_per_step': round(float(e2e_s.item()) * 1e3, 3), 'launches_per_step': e2e_launches,
-           'api': 'cspn_b200.propagate2d(cpu pinned tensors) -> C ABI cspn2d_fwd_f32_host'}
+           'api': 'cspn_b200.propagate2d(cpu pinned tensors) -> C ABI cspn2d_fwd_f32_host', 'host_numa_binding': numa}
     same = bool(torch.equal(out_h, out.cpu()))
 
-    # ---- optional: what the north_star calls "NCCL only for the final gather" (outside the timed value) ----
+    # ---- the north_star's "NCCL only for the final gather" (eval.py:117), outside the timed value: three ways --------
     gather = None
     if world > 1:
+        from cspn_b200.gather import ChunkedGather, FusedGather
+
+        def timed(fn, reps=5, warm=3):
+            for _ in range(warm):
+                fn()
+            barrier()
+            ev0.record()
+            for _ in range(reps):
+                fn()
+            ev1.record()
+            barrier()
+            t = torch.tensor([ev0.elapsed_time(ev1) / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
         full = torch.empty(world * B_PER_GPU, 1, H, W, device=dev)
-        for _ in range(5):
-            dist.all_gather_into_tensor(full, out)
-        barrier()
-        ev0.record()
-        for _ in range(5):
-            o = step()
-            dist.all_gather_into_tensor(full, o)
-        ev1.record()
-        barrier()
-        gms = torch.tensor([ev0.elapsed_time(ev1) / 5], device=dev)
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {'ms_per_step_with_all_gather': round(float(gms.item()), 4),
-                  'mpx_s_with_all_gather': round(world * px / (float(gms.item()) * 1e-3) / 1e6, 1),
-                  'bytes_received_per_rank': (world - 1) * px * 4}
+        serial_ms = timed(lambda: dist.all_gather_into_tensor(full, step()))
+        gather = {'bytes_received_per_rank': (world - 1) * px * 4,
+                  'serial_nccl': {'ms_per_step': round(serial_ms, 4), 'what': 'kernel, then all_gather_into_tensor'}}
+        ref_full = full.clone()
+        try:
+            cg = ChunkedGather(B_PER_GPU, 1, H, W, dev, n_chunks=4)
+            chunk_ms = timed(lambda: cg.propagate(g, d, s, ITERS, NORM, algo))
+            gather['chunked_nccl'] = {'ms_per_step': round(chunk_ms, 4), 'matches_serial': bool(torch.equal(cg.as_rank_major(), ref_full)),
+                                      'what': '4 chunks of 8 images: kernel of chunk i+1 overlaps the all-gather of chunk i'}
+        except Exception as e:
+            gather['chunked_nccl'] = {'error': str(e)[:200]}
+        try:
+            fg = FusedGather(B_PER_GPU, 1, H, W, dev)
+            fused_ms = timed(lambda: fg.propagate(g, d, s, ITERS, NORM))
+            res = fg.propagate(g, d, s, ITERS, NORM)
+            torch.cuda.synchronize()
+            gather['fused_epilogue'] = {'ms_per_step': round(fused_ms, 4), 'mode': fg.mode, 'matches_serial': bool(torch.equal(res, ref_full)),
+                                        'what': 'cspn2d_fwd_gather_f32: the kernel epilogue stores each tile into every GPU\'s gather buffer '
+                                                '(symmetric memory over NVLink), one barrier across ranks after it'}
+        except Exception as e:
+            gather['fused_epilogue'] = {'error': str(e)[:300]}
+        best = min((v['ms_per_step'], k) for k, v in gather.items() if isinstance(v, dict) and 'ms_per_step' in v)
+        gather['ms_per_step_with_all_gather'] = best[0]
+        gather['best'] = best[1]
+        gather['mpx_s_with_all_gather'] = round(world * px / (best[0] * 1e-3) / 1e6, 1)
+        gather['limiter'] = (f'each GPU receives {(world - 1) * px * 4 / 1e6:.0f} MB per step over NVLink: '
+                             f'>= {(world - 1) * px * 4 / 900e9 * 1e3:.3f} ms at 900 GB/s per direction')
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_leg()
+    configs = None
+    if rank == 0 and world == 1:
+        if not args.no_other_configs:
+            configs = other_configs(dev, peak, clocks.max_mhz)
+        if not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_leg()
 
     if rank == 0:
+        cfg = workload_config(world)
         line = {
             'metric': METRIC, 'value': round(value, 1), 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'2D CSPN 3x3, {ITERS} iters, {NORM}, with sparse depth, batch {B_PER_GPU}x{W}x{H} '
-                                   f'per GPU (BASELINE configs[1]; N=8 is configs[4])',
-                       'global_batch': world * B_PER_GPU, 'parallelism': f'dp{world} (independent images per rank)',
-                       'l2': 'inputs per step (602.7 MB/GPU) exceed the 126 MB L2; no flush needed',
-                       'algo': algo_used, 'plan': plan},
+            'config': cfg,
+            'detail': {'l2': 'inputs per step (602.7 MB/GPU) exceed the 126 MB L2; no flush needed', 'algo': algo_used, 'plan': plan},
             'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e,
             'gpu_launches': world * args.steps * launches_per_step,
             'clocks': clocks.summary(), 'e2e_matches_device_path': same,
         }
+        if configs:
+            line['configs'] = configs
         if gather:
             line['gather'] = gather
         emit(line)

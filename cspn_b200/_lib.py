@@ -20,6 +20,7 @@ SIGNATURES = {
     'cspn2d_workspace_bytes': (_sz, [_i] * 6),
     'cspn2d_fwd_f32': (_i, [_vp] * 4 + [_i] * 8 + [_vp, _sz, _vp]),
     'cspn2d_fwd_f32_host': (_i, [_vp] * 4 + [_i] * 9),
+    'cspn2d_fwd_gather_f32': (_i, [_vp] * 5 + [_i, _vp] + [_i] * 7 + [_vp, _sz, _vp]),
     'cspn2d_bwd_workspace_bytes': (_sz, [_i] * 5),
     'cspn2d_bwd_f32': (_i, [_vp] * 6 + [_i] * 7 + [_vp, _sz, _vp]),
     'cspn3d_workspace_bytes': (_sz, [_i] * 6),

@@ -126,6 +126,33 @@ int cspn2d_fwd_f32(const float* guidance, const float* blur, const float* sparse
     return rc;
 }
 
+int cspn2d_fwd_gather_f32(const float* guidance, const float* blur, const float* sparse, float* out, float* const* peer_out,
+                          int n_peer, float* multicast_out, int B, int C, int H, int W, int guidance_channels, int iters,
+                          int norm_type, void* workspace, size_t workspace_bytes, cspn_stream_t stream) {
+    clear_error();
+    g_last_launches = 0;
+    int rc = check2d(guidance, blur, out, B, C, H, W, guidance_channels, iters, norm_type, CSPN_ALGO_CLUSTER);
+    if (rc != CSPN_OK) return rc;
+    if (n_peer < 0 || n_peer > 7 || (n_peer > 0 && !peer_out)) { set_error("n_peer must be 0..7 with a pointer array"); return CSPN_ERR_INVALID_ARGUMENT; }
+    for (int i = 0; i < n_peer; ++i)
+        if (!peer_out[i] || (reinterpret_cast<uintptr_t>(peer_out[i]) & 15)) { set_error("peer_out[%d] is null or not 16-byte aligned", i); return CSPN_ERR_INVALID_ARGUMENT; }
+    if (reinterpret_cast<uintptr_t>(multicast_out) & 15) { set_error("multicast_out is not 16-byte aligned"); return CSPN_ERR_INVALID_ARGUMENT; }
+    if (iters == 0) { set_error("the fused gather needs prop_time >= 1"); return CSPN_ERR_UNSUPPORTED; }
+    DeviceGuard guard(device_of(blur));
+    if (!guard.ok) { set_error("cannot select the device of `blur`"); return CSPN_ERR_CUDA; }
+    Problem2D p{guidance, blur, sparse, out, B, C, H, W, guidance_channels, iters, norm_type == CSPN_NORM_8SUM_ABS};
+    char why[256] = "";
+    if (!cluster2d_supported(p, why, sizeof(why))) {
+        set_error("the fused gather runs in the cluster kernel's epilogue, which cannot take this problem: %s", why);
+        return CSPN_ERR_UNSUPPORTED;
+    }
+    g_last_algo = CSPN_ALGO_CLUSTER;
+    int launches = 0;
+    rc = cluster2d_forward(p, workspace, workspace_bytes, (cudaStream_t)stream, &launches, peer_out, n_peer, multicast_out);
+    g_last_launches = launches;
+    return rc;
+}
+
 size_t cspn2d_bwd_workspace_bytes(int B, int C, int H, int W, int iters) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || iters < 0) return 0;
     return bwd2d_workspace_bytes(B, C, H, W, iters);

@@ -60,7 +60,9 @@ int generic2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_
 
 bool cluster2d_supported(const Problem2D& p, char* why, int why_len);
 size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters);
-int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches);
+// peer_out / mc_out: additional destinations of the final result (fused gather), see cspn2d_fwd_gather_f32
+int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches,
+                      float* const* peer_out = nullptr, int n_peer = 0, float* mc_out = nullptr);
 int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len);
 int cluster2d_plan_json(int H, int W, int iters, char* buf, int len);
 // staged (opt-in, see cspn2d_bwd.cu): the forward keeping every iterate, and the adjoint sweep, on the cluster kernel

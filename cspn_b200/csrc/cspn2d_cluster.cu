@@ -53,6 +53,12 @@ struct ClusterParams {
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_bands, n_tasks;
     int zero;             // always 0; a value ptxas cannot fold (see wait_token)
+    // fused final gather (cspn2d_fwd_gather_f32): the result is ALSO stored to these destinations -- the same block in
+    // the gather buffers of the other GPUs (peer-mapped pointers over NVLink) and / or one NVLS multicast address that
+    // the switch replicates to every GPU (multimem.st) -- tile by tile, while the kernel computes the next tiles
+    float* out_peer[7];
+    int n_peer;
+    float* out_mc;
     unsigned long long* trace;   // -DCSPN_TRACE builds only (tools/trace_cluster.py): per-warp clock stamps, else null
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
@@ -1161,8 +1167,17 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 const int y = y_thr + r;
                 if (y >= uy0 && y < uy1) {
                     const float4 v = make_float4(d[r][0], d[r][1], d[r][2], d[r][3]);
-                    if constexpr (MODE == kForward) __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x_thr), v);
-                    else *reinterpret_cast<float4*>(out + (size_t)y * W + x_thr) = v;   // read again by the next pass
+                    if constexpr (MODE == kForward) {
+                        const size_t off = (size_t)bc * HW + (size_t)y * W + x_thr;
+                        __stcs(reinterpret_cast<float4*>(prm.out + off), v);
+                        for (int e = 0; e < prm.n_peer; ++e)        // peer GPUs' gather buffers (NVLink stores)
+                            __stcs(reinterpret_cast<float4*>(prm.out_peer[e] + off), v);
+                        if (prm.out_mc)                             // NVLS: one store, replicated by the switch
+                            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(prm.out_mc + off),
+                                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    } else {
+                        *reinterpret_cast<float4*>(out + (size_t)y * W + x_thr) = v;   // read again by the next pass
+                    }
                 }
             }
         }
@@ -1511,8 +1526,10 @@ int plan_for_launch(const Problem2D& p, Plan& plan) {
 // One pass = one launch of `fn` with plan `pp`.  `start` plays the role of blur_depth (kAdjoint: lambda's start value),
 // `init` continues from an earlier pass (kForward / kStoreSteps), `iter_out` / `iter_stride` say where every step but
 // the last is written (kStoreSteps / kAdjoint), the last step goes to `out`.
+struct Scatter { float* const* peer = nullptr; int n_peer = 0; float* mc = nullptr; };
+
 int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const float* start, const float* init, float* out,
-                float* iter_out, long long iter_stride, cudaStream_t stream) {
+                float* iter_out, long long iter_stride, cudaStream_t stream, const Scatter& sc = Scatter()) {
     const KernelCfg& k = configs()[pp.cfg];
     // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane.  The descriptor is a
     // pure function of (base pointer, shape, box): serving loops call with the same buffers again and again, so the last
@@ -1562,6 +1579,9 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     prm.n_bands = pp.n_bands;
     prm.zero = 0;
     prm.trace = g_trace;
+    prm.n_peer = sc.n_peer;
+    for (int i = 0; i < 7; ++i) prm.out_peer[i] = i < sc.n_peer ? sc.peer[i] : nullptr;
+    prm.out_mc = sc.mc;
     const long tasks = (long)p.B * p.C * pp.n_strips * pp.n_bands;
     if (tasks > 2147483647L) { set_error("too many tasks"); return CSPN_ERR_UNSUPPORTED; }
     prm.n_tasks = (int)tasks;
@@ -1595,7 +1615,8 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
 
 }  // namespace
 
-int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches) {
+int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches, float* const* peer_out,
+                      int n_peer, float* mc_out) {
     Plan plan;
     int rc = plan_for_launch(p, plan);
     if (rc != CSPN_OK) return rc;
@@ -1611,7 +1632,9 @@ int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_
         // passes alternate between the workspace and `out` such that the last one lands in `out`
         float* dst = ((plan.n_pass - 1 - ip) & 1) ? static_cast<float*>(ws) : p.out;
         const bool general = pp.n_bands > 1 || prev != nullptr;
-        rc = launch_pass(p, pp, configs()[pp.cfg].fn[general ? 1 : 0][p.norm_abs ? 1 : 0], p.blur, prev, dst, nullptr, 0, stream);
+        Scatter sc;
+        if (ip == plan.n_pass - 1) { sc.peer = peer_out; sc.n_peer = n_peer; sc.mc = mc_out; }   // only the final result travels
+        rc = launch_pass(p, pp, configs()[pp.cfg].fn[general ? 1 : 0][p.norm_abs ? 1 : 0], p.blur, prev, dst, nullptr, 0, stream, sc);
         if (rc != CSPN_OK) return rc;
         ++*launches;
         prev = dst;

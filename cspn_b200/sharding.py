@@ -34,3 +34,31 @@ def gather_outputs(local_out, batch, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off (and, by first touch, the pinned host
+    buffers it allocates afterwards).  Eight ranks each pushing 50 GB/s of pinned H2D from whatever socket the scheduler
+    put them on lose a third of that bandwidth (round 1: e2e weak-scaling efficiency 0.65 at 8 GPUs).  Returns a short
+    description, or None when the topology cannot be read (containers without sysfs PCI entries): then nothing changes."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f'numa node {node} ({len(cpus)} cpus) for GPU {bdf}'
+    except Exception:
+        return None

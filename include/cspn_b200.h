@@ -90,6 +90,20 @@ CSPN_API int cspn2d_fwd_f32_host(const float* guidance, const float* blur, const
                         int B, int C, int H, int W, int guidance_channels, int iters, int norm_type,
                         int algo, int device);
 
+/* ---- 2D forward fused with the final gather of a data-parallel run -----------------------------------------------
+ * The reference gathers the replicas' outputs with nn.DataParallel (eval.py:117); one process per GPU does it with an
+ * all-gather AFTER the kernel.  Here the kernel's epilogue stores every result tile to `out` and, tile by tile while it
+ * goes on computing, to each peer_out[i] (the same [B][C][H][W] block inside the gather buffers of the other GPUs: peer
+ * pointers mapped over NVLink, e.g. from a CUDA symmetric-memory allocation) and / or to multicast_out (an NVLS multicast
+ * address: one multimem.st, replicated to all GPUs by the switch).  n_peer 0..7, multicast_out may be NULL; all
+ * destinations 16-byte aligned.  Cluster kernel only (CSPN_ERR_UNSUPPORTED otherwise); workspace as for
+ * CSPN_ALGO_CLUSTER.  The caller orders the remote stores before their consumers (a barrier across ranks after the
+ * kernel: stores to peers are visible system-wide at kernel completion). */
+CSPN_API int cspn2d_fwd_gather_f32(const float* guidance, const float* blur, const float* sparse, float* out,
+                          float* const* peer_out, int n_peer, float* multicast_out,
+                          int B, int C, int H, int W, int guidance_channels, int iters, int norm_type,
+                          void* workspace, size_t workspace_bytes, cspn_stream_t stream);
+
 /* ---- 2D backward (adjoint of the above; reference: autograd through cspn.py:42-83, used by
  * train.py:198).  grad_guidance [B][guidance_channels][H][W] (channels >= 8 are zero-filled),
  * grad_blur [B][C][H][W].  Either may be NULL.  Needs the forward inputs again. */
