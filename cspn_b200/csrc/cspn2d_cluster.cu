@@ -52,7 +52,6 @@ struct ClusterParams {
     long long iter_stride;  // ... and the (signed) distance in floats to the plane of the next step; the LAST step goes to `out`
     int C, H, W, gch, iters, norm_abs;
     int n_strips, n_bands, n_tasks;
-    int zero;             // always 0; a value ptxas cannot fold (see wait_token)
     // fused final gather (cspn2d_fwd_gather_f32): the result is ALSO stored to these destinations -- the same block in
     // the gather buffers of the other GPUs (peer-mapped pointers over NVLink) and / or one NVLS multicast address that
     // the switch replicates to every GPU (multimem.st) -- tile by tile, while the kernel computes the next tiles
@@ -97,25 +96,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
-}
-// The first probe carries no dependency (ptxas issues it early, its latency overlaps the FMAs behind it); the decision
-// to go on is what depends on `token` (a run-time zero derived from accumulators, see wait_token).
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done;
-}
-__device__ __forceinline__ void mbar_wait_dep(uint32_t bar, uint32_t parity, uint32_t token) {
-    uint32_t done = mbar_try(bar, parity) | token;
-    while (!done) done = mbar_try(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -172,7 +152,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 //                             shift of cspn.py:105-129 cannot ride on the box origin; the row shift dy_k does)
 //   then xch[2][2*NW+2][TW]   row-exchange buffers (parity, slot, column)
 //   then cbuf[RB][TW]         folded constant term c' of the current task
-//   then mbarriers            tma, full[group 0][parity 0,1], full[group 1][parity 0,1]
+//   then 3 mbarriers          tma, full[0], full[1]
 //
 // Arithmetic is scalar FFMA on purpose.  fma.rn.f32x2 (FFMA2, new on sm_100) was tried with pixel pairs in 64-bit
 // registers: with 160 weight registers live per thread it sustains only ~0.22 FFMA2/clk per sub-partition (715 cycles
@@ -186,16 +166,6 @@ struct Cfg {
     static constexpr int TW = 32 * PC;   // tile (strip) width
     static constexpr int TWP = TW + 8;   // staged row pitch: 4 apron columns on each side
     static constexpr int kSlots = 2 * NW + 2;
-    // Warp groups (-DCSPN_GROUPS=2): the upper and the lower half of the CTA's warps synchronise on their own mbarrier
-    // pair and run about half a step apart.  Warps w and w + NW/2 share an SM sub-partition, so while one of them sits
-    // in the latency-bound part of its step (barrier wait -> halo rows -> publish) the other one is in its FMA-bound part:
-    // with one CTA-wide barrier all warps reach that bubble together and the sub-partition idles (~170 cycles per step,
-    // profiles/r02_trace_*.txt).
-#ifndef CSPN_GROUPS
-#define CSPN_GROUPS 1
-#endif
-    static constexpr int kGroups = (CSPN_GROUPS == 2 && NW >= 4) ? 2 : 1;
-    static constexpr int kGroupWarps = NW / kGroups;
     // exchange rows carry 4 zero floats on each side: a thread reads the x-neighbours of a halo row straight from the
     // row (lane 0 / 31 find the zeros), so the halo taps need neither shuffles nor selects
     static constexpr int TWX = TW + 8;
@@ -220,19 +190,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// The two x-neighbours of a row of PC pixels: the last pixel of lane l-1 and the first of lane l+1.  Outside the tile
-// the neighbour is 0: either the image border (zero padding) or strip halo that decays.
-template <int PC>
-__device__ __forceinline__ void row_edges(const float (&v)[PC], float (&ed)[2], bool first_lane, bool last_lane) {
-#ifdef CSPN_ABLATE_NO_SHFL   // timing experiment only: wrong results
-    ed[0] = v[PC - 1]; ed[1] = v[0]; return;
-#endif
-    const float l = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
-    const float r = __shfl_down_sync(0xffffffffu, v[0], 1);
-    ed[0] = first_lane ? 0.f : l;
-    ed[1] = last_lane ? 0.f : r;
-}
-
 // Extended row view: (-1) = left neighbour, (0..PC-1) = own pixels, (PC) = right neighbour.
 template <int PC>
 struct Row {
@@ -244,26 +201,6 @@ struct Row {
 // Channel of the tap that reads the pixel at offset (dy, dx) (channel order of cspn.py, see common.cuh):
 //   (+1,+1)=0 (+1,0)=1 (+1,-1)=2 (0,+1)=3 (0,-1)=4 (-1,+1)=5 (-1,0)=6 (-1,-1)=7
 __host__ __device__ constexpr int tap_of(int dy, int dx) { return dy == 1 ? 1 - dx : (dy == 0 ? (dx == 1 ? 3 : 4) : 6 - dx); }
-
-// Scatter one source row into the accumulators of one destination row.  `src(jx)`, jx = -1..PC, is the extended
-// source row; it sits SRC_DY rows below the destination row whose weights are `w` (+1: the row below, 0: the same
-// row, -1: the row above).  The loop nest is SOURCE-major: the FMAs that consume one source value are adjacent and
-// write different accumulators, so none depends on its predecessor and the shared operand can come from the
-// operand-reuse cache (three distinct register operands per FFMA run at ~2/3 rate on the register file).
-template <int PC, int SRC_DY, typename Src>
-__device__ __forceinline__ void scatter_row(const float (&w)[PC][8], const Src& src, float (&acc)[PC]) {
-#pragma unroll
-    for (int jx = -1; jx <= PC; ++jx) {
-        const float xv = src(jx);
-#pragma unroll
-        for (int dx = 1; dx >= -1; --dx) {
-            const int j = jx - dx;                       // destination column that reads this source with offset dx
-            if (j < 0 || j >= PC) continue;
-            if (SRC_DY == 0 && dx == 0) continue;         // no centre tap
-            acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]);
-        }
-    }
-}
 
 __device__ __forceinline__ void load_row_smem(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
@@ -303,26 +240,9 @@ struct Xch {
     // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
     // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
     bool remote_up, remote_dn, sig_tx, sig;
-    uint32_t cross_bar;   // two warp groups: full[0] of the OTHER group, for the warp whose row that group reads
-    bool cross;
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
-    uint32_t zero;        // 0 at run time, opaque at compile time
 };
-
-// -DCSPN_WAIT_DEP: a zero that DEPENDS on the given accumulators, added to the barrier address: the mbarrier wait cannot be
-// scheduled before the FMAs that produce them (ptxas otherwise sinks the pre-wait FMAs below the wait).
-template <int PC>
-__device__ __forceinline__ uint32_t wait_token(const Xch& x, const float (&a)[PC], const float (&b)[PC]) {
-#ifdef CSPN_WAIT_DEP
-    uint32_t t = 0;
-#pragma unroll
-    for (int j = 0; j < PC; ++j) t |= __float_as_uint(a[j]) | __float_as_uint(b[j]);
-    return t & x.zero;
-#else
-    return 0u;
-#endif
-}
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
 // halo slots through DSMEM), then signal full[PAR].  Branch-free: roles are predicates.
@@ -341,77 +261,27 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     __syncwarp();
     mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
     mbar_arrive_if(bar, x.sig);
-    if constexpr (K::kGroups == 2) mbar_arrive_if(x.cross_bar + 8 * PAR, x.cross);   // my row is read by the other group
 }
 
-// One propagation step d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes
-// into PAR^1 (not on the last step).  Two register sets alternate as input and output: nothing is copied.
-// On entry dout already holds c' (the accumulators' seed); on exit din -- dead by then, and the output set of the next
-// step -- is re-seeded with c' from shared memory, so that load has a whole exchange to land.
+// ---- one propagation step ---------------------------------------------------------------------------------------
+// d_it (din, with x-edges ein) -> d_{it+1} (dout, eout).  Reads exchange buffer PAR, publishes into PAR^1 (not on the last
+// step).  Two register sets alternate as input and output: nothing is copied.
 //
-// Ordering is what makes the exchange free: every source row the thread owns is scattered into the accumulators
-// BEFORE the mbarrier wait; after the wait only the rows above / below the patch remain (3 taps of the two boundary
-// rows), then the new boundary rows are published at once and the x-edges of the new rows (shuffles) are computed in
-// the tail, off the critical path of the other warps.
-template <int PR, int PC, int NW, int PAR, bool PUBLISH>
-__device__ __forceinline__ void iterate(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
-                                        float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
-                                        float (&eout)[PR][2]) {
-    using K = Cfg<PR, PC, NW>;
-    // ---- before the wait: the own-source taps of the two BOUNDARY rows (they gate the publish) -----------------
-    {
-        const Row<PC> r0{din[0], ein[0]}, r1{din[1], ein[1]}, rp{din[PR - 2], ein[PR - 2]}, rl{din[PR - 1], ein[PR - 1]};
-        scatter_row<PC, 0>(w[0], r0, dout[0]);
-        scatter_row<PC, +1>(w[0], r1, dout[0]);
-        scatter_row<PC, 0>(w[PR - 1], rl, dout[PR - 1]);
-        scatter_row<PC, -1>(w[PR - 1], rp, dout[PR - 1]);
-    }
-    // ---- the neighbours' rows ----------------------------------------------------------------------------
-#ifndef CSPN_ABLATE_NO_SYNC  // timing experiment only: wrong results
-    CSPN_STAMP(x, 5 + 3 * x.step);
-    mbar_wait(x.bar_full0 + 8 * PAR, phase);
-    CSPN_STAMP(x, 6 + 3 * x.step);
-#endif
-    {
-        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
-        float u[PC], ue[2], d[PC], de[2];
-        load_row_smem(p + (2 * wy) * K::TWX, u);        // row above my patch
-        load_row_smem(p + (2 * wy + 3) * K::TWX, d);    // row below my patch
-        row_edges<PC>(u, ue, x.first_lane, x.last_lane);
-        row_edges<PC>(d, de, x.first_lane, x.last_lane);
-        scatter_row<PC, -1>(w[0], Row<PC>{u, ue}, dout[0]);
-        scatter_row<PC, +1>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1]);
-    }
-    // ---- interior rows: independent of the exchange; placed here so that their FMAs fill the latency of the
-    // load -> shuffle -> select -> FMA chain above instead of leaving the sub-partition idle behind the barrier
-#pragma unroll
-    for (int r = 1; r <= PR - 2; ++r) {
-        scatter_row<PC, -1>(w[r], Row<PC>{din[r - 1], ein[r - 1]}, dout[r]);
-        scatter_row<PC, 0>(w[r], Row<PC>{din[r], ein[r]}, dout[r]);
-        scatter_row<PC, +1>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r]);
-    }
-    if constexpr (PUBLISH) {
-#ifndef CSPN_ABLATE_NO_SYNC
-        publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
-        CSPN_STAMP(x, 7 + 3 * x.step);
-#endif
-        // ---- tail: seed the next step's accumulators, x-edges of the new rows ---------------------------------
-#pragma unroll
-        for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
-#pragma unroll
-        for (int r = 0; r < PR; ++r) row_edges<PC>(dout[r], eout[r], x.first_lane, x.last_lane);
-    }
-}
-
-// ---- step, second formulation (-DCSPN_STEP=2) ------------------------------------------------------------------
-// Same arithmetic, different critical path.  What a neighbour waits for is my new boundary rows; what they wait for is
-// the neighbours' previous boundary rows.  So: (A) every tap fed by one of my OWN rows -- 136 of the 160 FMAs -- goes
-// before the mbarrier wait, interior rows are complete there and their x-edges are shuffled at once; (B) after the wait
-// only the two halo rows remain: their x-neighbours are read from the padded exchange row itself (no shuffle, no
-// select in the chain wait -> LDS -> 3 FMA -> STS), and the boundary rows are published immediately; (C) the tail
-// shuffles the two boundary rows and re-seeds the dead register set with c'.
-// Tile-edge lanes: the shuffled-in value of lane 0 (31) is meaningless; instead of zeroing it with a select per row
-// and step, the three taps that would consume it are predicated off (exactly the reference's zero padding, NaN-safe).
+// What a neighbour waits for is my new boundary rows; what they wait for is the neighbours' previous boundary rows.  So
+// after the mbarrier wait only the two halo rows remain to be added to the boundary rows: their x-neighbours are read
+// from the padded exchange row itself (no shuffle, no select in the chain wait -> LDS -> 3 FMA -> STS) and the boundary
+// rows are published at once.  ptxas schedules register arithmetic freely around the (volatile) barrier instructions and,
+// left to itself, sinks most FMAs between the wait and the publish; memory operations however keep their order relative
+// to the volatile asm statements, so the accumulators of the interior rows are seeded with c' (an LDS) only AFTER the
+// publish: none of their 96 FMAs can run before it.  Per step: wait -> 24 halo FMAs -> publish -> [96 interior FMAs of
+// this step, then the 40 own-row FMAs of the next step's boundary rows] -> wait.  On entry dout[0] and dout[PR-1] hold c'.
+// Tile-edge lanes: the shuffled-in value of lane 0 (31) is meaningless; instead of zeroing it with a select per row and
+// step, the three taps that would consume it are predicated off (exactly the reference's zero padding, NaN-safe).
+// Measured alternatives (all own-row FMAs before the wait, wait forced late through a data dependency, source-major
+// order over all interior rows, two phase-shifted warp groups): profiles/r02_tuning_log.md.
+// scatter_row2: one source row into the accumulators of one destination row.  `src(jx)`, jx = -1..PC, is the extended
+// source row; it sits SRC_DY rows below the destination row whose weights are `w`.  The loop nest is SOURCE-major: the FMAs
+// that consume one source value are adjacent and write different accumulators (operand-reuse cache, no dependent pairs).
 template <int PC, int SRC_DY, bool GUARD, typename Src>
 __device__ __forceinline__ void scatter_row2(const float (&w)[PC][8], const Src& src, float (&acc)[PC], bool use_left,
                                              bool use_right) {
@@ -430,74 +300,12 @@ __device__ __forceinline__ void scatter_row2(const float (&w)[PC][8], const Src&
         }
     }
 }
-// The taps one source value `xv` (column sx of a row SRC_DY rows below the destination row) feeds in that destination row.
-template <int PC, int SRC_DY>
-__device__ __forceinline__ void taps_of_source(const float (&w)[PC][8], int sx, float xv, float (&acc)[PC], bool use_left,
-                                               bool use_right) {
-#pragma unroll
-    for (int dx = 1; dx >= -1; --dx) {
-        const int j = sx - dx;
-        if (j < 0 || j >= PC) continue;
-        if (SRC_DY == 0 && dx == 0) continue;
-        if (sx < 0) { if (use_left) acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]); }
-        else if (sx >= PC) { if (use_right) acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]); }
-        else acc[j] = fmaf(w[j][tap_of(SRC_DY, dx)], xv, acc[j]);
-    }
-}
 template <int PC>
 __device__ __forceinline__ void row_edges_raw(const float (&v)[PC], float (&ed)[2]) {
     ed[0] = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);     // lane 0 gets its own value back: never consumed (guarded taps)
     ed[1] = __shfl_down_sync(0xffffffffu, v[0], 1);
 }
 
-template <int PR, int PC, int NW, int PAR, bool PUBLISH>
-__device__ __forceinline__ void iterate2(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
-                                         float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
-                                         float (&eout)[PR][2]) {
-    using K = Cfg<PR, PC, NW>;
-    const bool ul = !x.first_lane, ur = !x.last_lane;
-    // ---- A: own source rows ----------------------------------------------------------------------------------
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-        if (r > 0) scatter_row2<PC, -1, true>(w[r], Row<PC>{din[r - 1], ein[r - 1]}, dout[r], ul, ur);
-        scatter_row2<PC, 0, true>(w[r], Row<PC>{din[r], ein[r]}, dout[r], ul, ur);
-        if (r + 1 < PR) scatter_row2<PC, +1, true>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r], ul, ur);
-        if (PUBLISH && r > 0 && r + 1 < PR) row_edges_raw<PC>(dout[r], eout[r]);   // interior row r is final
-    }
-    // ---- B: the neighbours' rows -------------------------------------------------------------------------------
-#ifndef CSPN_ABLATE_NO_SYNC
-    mbar_wait(x.bar_full0 + 8 * PAR, phase);
-#endif
-    {
-        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
-        const float* pu = p + (2 * wy) * K::TWX;          // row above my patch
-        const float* pd = p + (2 * wy + 3) * K::TWX;      // row below my patch
-        float u[PC], ue[2], d[PC], de[2];
-        load_row_smem(pu, u);
-        load_row_smem(pd, d);
-        ue[0] = pu[-1]; ue[1] = pu[PC];                   // pad floats are zero at the tile edges
-        de[0] = pd[-1]; de[1] = pd[PC];
-        scatter_row2<PC, -1, false>(w[0], Row<PC>{u, ue}, dout[0], true, true);
-        scatter_row2<PC, +1, false>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1], true, true);
-    }
-    if constexpr (PUBLISH) {
-#ifndef CSPN_ABLATE_NO_SYNC
-        publish<PR, PC, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
-#endif
-        // ---- C: tail ------------------------------------------------------------------------------------------
-        row_edges_raw<PC>(dout[0], eout[0]);
-        row_edges_raw<PC>(dout[PR - 1], eout[PR - 1]);
-#pragma unroll
-        for (int r = 0; r < PR; ++r) load_row_smem(x.cbuf + r * K::TW, din[r]);
-    }
-}
-
-// ---- step, third formulation (-DCSPN_STEP=3): the second one with the ORDER pinned -----------------------------------
-// ptxas schedules register arithmetic freely around the (volatile) barrier instructions, and left to itself it sinks most
-// of the FMAs between the wait and the publish.  Memory operations, however, keep their order relative to the volatile
-// asm statements: the accumulators of the interior rows are therefore seeded with c' (an LDS) only AFTER the publish, so
-// none of their 96 FMAs can run before it.  Per step: wait -> 24 halo FMAs -> publish -> [96 interior FMAs of this step,
-// then the 40 own-row FMAs of the next step's boundary rows] -> wait.  On entry dout[0] and dout[PR-1] hold c'.
 template <int PR, int PC, int NW, int PAR, bool PUBLISH>
 __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                          float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
@@ -512,7 +320,7 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
     // ---- B: the neighbours' rows, then publish at once ---------------------------------------------------------------
 #ifndef CSPN_ABLATE_NO_SYNC
     CSPN_STAMP(x, 5 + 3 * x.step);
-    mbar_wait_dep(x.bar_full0 + 8 * PAR, phase, wait_token<PC>(x, dout[0], dout[PR - 1]));
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
     CSPN_STAMP(x, 6 + 3 * x.step);
 #endif
     {
@@ -538,25 +346,6 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         row_edges_raw<PC>(dout[PR - 1], eout[PR - 1]);
     }
     // ---- C: interior rows (their seed is loaded after the publish: see above) ---------------------------------------------
-#ifdef CSPN_SRC_MAJOR
-    // source-major over ALL interior destination rows: the up to 8 FMAs that read one source value are adjacent, so the
-    // value can sit in the operand-reuse cache for all of them (register-file bandwidth is what limits this FMA stream)
-#pragma unroll
-    for (int r = 1; r + 1 < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
-#pragma unroll
-    for (int sr = 0; sr < PR; ++sr) {
-        const Row<PC> src{din[sr], ein[sr]};
-#pragma unroll
-        for (int jx = 0; jx <= PC + 1; ++jx) {
-            const int sx = jx <= PC - 1 ? jx : (jx == PC ? -1 : PC);
-            const float xv = src(sx);
-            if (sr - 1 >= 1 && sr - 1 + 1 < PR) taps_of_source<PC, +1>(w[sr - 1], sx, xv, dout[sr - 1], ul, ur);
-            if (sr >= 1 && sr + 1 < PR) taps_of_source<PC, 0>(w[sr], sx, xv, dout[sr], ul, ur);
-            if (sr + 1 >= 1 && sr + 2 < PR) taps_of_source<PC, -1>(w[sr + 1], sx, xv, dout[sr + 1], ul, ur);
-        }
-        if constexpr (PUBLISH) { if (sr >= 2 && sr - 1 + 1 < PR) row_edges_raw<PC>(dout[sr - 1], eout[sr - 1]); }   // row sr-1 is final
-    }
-#else
 #pragma unroll
     for (int r = 1; r + 1 < PR; ++r) {
         load_row_smem(x.cbuf + r * K::TW, dout[r]);
@@ -565,27 +354,17 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         scatter_row2<PC, +1, true>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r], ul, ur);
         if constexpr (PUBLISH) row_edges_raw<PC>(dout[r], eout[r]);
     }
-#endif
     if constexpr (PUBLISH) {   // seeds of the next step's boundary rows, into the now dead input set
         load_row_smem(x.cbuf, din[0]);
         load_row_smem(x.cbuf + (PR - 1) * K::TW, din[PR - 1]);
     }
 }
 
-#ifndef CSPN_STEP
-#define CSPN_STEP 1
-#endif
 template <int PR, int PC, int NW, int PAR, bool PUBLISH>
 __device__ __forceinline__ void step_fwd(Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                          float (&din)[PR][PC], float (&ein)[PR][2], float (&dout)[PR][PC],
                                          float (&eout)[PR][2]) {
-#if CSPN_STEP == 3
     iterate3<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
-#elif CSPN_STEP == 2
-    iterate2<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
-#else
-    iterate<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
-#endif
 #ifdef CSPN_TRACE
     ++x.step;
 #endif
@@ -696,32 +475,21 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.step = 0;
 #endif
     xc.base = xch + 4 + lane * PC;     // 4 zero floats lead every exchange row
-    // barrier of group g, parity p: bar_full0 + 16 g + 8 p.  One group: everything on group 0.
-    constexpr int kGroups = K::kGroups, kGroupWarps = K::kGroupWarps;
-    const int group = wy / kGroupWarps;
-    const uint32_t bar_last_group = bar_full0 + 16 * (kGroups - 1);     // the group that owns the CTA's bottom rows
-    xc.bar_full0 = bar_full0 + 16 * group;
+    xc.bar_full0 = bar_full0;
     xc.has_up = crank > 0;
     xc.has_dn = crank + 1 < csize;
-    // my top row is read by the LAST group of the CTA above, my bottom row by the FIRST group of the CTA below
     xc.up_data = xc.has_up ? map_to_cta(smem_u32(xc.base + (K::kSlots - 1) * TWX), crank - 1) : 0u;
-    xc.up_bar = xc.has_up ? map_to_cta(bar_last_group, crank - 1) : 0u;
+    xc.up_bar = xc.has_up ? map_to_cta(bar_full0, crank - 1) : 0u;
     xc.dn_data = xc.has_dn ? map_to_cta(smem_u32(xc.base), crank + 1) : 0u;
     xc.dn_bar = xc.has_dn ? map_to_cta(bar_full0, crank + 1) : 0u;
-    // halo bytes my group's barrier receives per exchange, and the warp that arms them (the one that reads the halo)
-    const bool rx_up = xc.has_up && group == 0, rx_dn = xc.has_dn && group == kGroups - 1;
-    xc.rx_bytes = (uint32_t)((rx_up ? 1 : 0) + (rx_dn ? 1 : 0)) * TW * sizeof(float);
-    const bool armer = kGroups == 1 ? wy == 0 : (wy == 0 || wy == NW - 1);
+    xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
     xc.remote_up = xc.has_up && wy == 0;
     xc.remote_dn = xc.has_dn && wy == NW - 1;
-    xc.sig_tx = lane == 0 && armer && xc.rx_bytes != 0;
-    xc.sig = lane == 0 && !(armer && xc.rx_bytes != 0);
-    xc.cross = kGroups == 2 && lane == 0 && (wy == kGroupWarps - 1 || wy == kGroupWarps);
-    xc.cross_bar = bar_full0 + 16 * (1 - group);
+    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
+    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
-    xc.zero = (uint32_t)prm.zero;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -744,10 +512,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        for (int g = 0; g < K::kGroups; ++g) {     // a group's warps + (two groups) the adjacent warp of the other group
-            mbar_init(bar_full0 + 16 * g, K::kGroupWarps + (K::kGroups - 1));
-            mbar_init(bar_full0 + 16 * g + 8, K::kGroupWarps + (K::kGroups - 1));
-        }
+        mbar_init(bar_full0, NW);
+        mbar_init(bar_full0 + 8, NW);
         fence_barrier_init();
         fence_proxy_async();
         if (task < n_tasks) issue_stage(task);
@@ -768,6 +534,31 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         xch[(size_t)row * TWX + (c < 4 ? c : TW + c)] = 0.f;
     }
     cluster_wait();
+
+    // blur / sparse rows of task t, straight from global into registers (aligned float4, read once).  Requested one task
+    // ahead: after the step loop the 160 weight registers are dead, so the 2 x PR float4 in flight cost nothing, and the
+    // latency (HBM: nothing prefetches them) hides behind the epilogue stores, the index arithmetic and the TMA wait.
+    float4 dv[PR], sv[PR];
+    auto request_rows = [&](int t) {
+        const int strip_t = t % prm.n_strips, q_t = t / prm.n_strips;
+        const int bc_t = GENERAL ? q_t / prm.n_bands : q_t;
+        const int y0 = (GENERAL ? prm.band_y0[q_t % prm.n_bands] : 0) + thr_dy;
+        const int x0 = prm.tile_x0[strip_t] + lane * PC;
+        const float* bl = prm.blur + (size_t)bc_t * HW;
+        const float* sp = prm.sparse ? prm.sparse + (size_t)(bc_t / prm.C) * HW : nullptr;
+        const bool cin = (x0 >= 0) && (x0 < W);
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+            const int y = y0 + r;
+            dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sv[r] = dv[r];
+            if (cin && y < H) {
+                dv[r] = __ldg(reinterpret_cast<const float4*>(bl + (size_t)y * W + x0));
+                if (sp) sv[r] = __ldg(reinterpret_cast<const float4*>(sp + (size_t)y * W + x0));
+            }
+        }
+    };
+    if (task < n_tasks) request_rows(task);
 
     uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
     bool first = true;
@@ -795,149 +586,23 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const float* blur = prm.blur + (size_t)bc * HW;
         const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
 
-#ifndef CSPN_PROLOGUE
-#define CSPN_PROLOGUE 2
-#endif
-#if CSPN_PROLOGUE == 2
-        // ---- prologue, pipelined: affinity normalisation + mask folding (cspn.py:85-144, 63-64) ---------------------------
-        // blur / sparse rows are REQUESTED first (straight from global: aligned, read once, prefetched into L2 by the
-        // previous task; W % 4 == 0 and x_thr % 4 == 0, so a float4 is entirely inside or outside the image) and CONSUMED
-        // kLag rows later: phase 1 of a row (gather the 8 affinities, sum |a|, reciprocal) needs only the staged guidance,
-        // phase 2 (mask folding, c') needs the loaded values.  Their L2 latency hides under phase 1 of the first rows.
-        const bool col_in = (x_thr >= 0) && (x_thr < W);
-        float4 dv[PR], sv[PR];
-#pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            const int y = y_thr + r;
-            dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            sv[r] = dv[r];
-            if (col_in && y < H) {
-                dv[r] = __ldg(reinterpret_cast<const float4*>(blur + (size_t)y * W + x_thr));
-                if (sparse) sv[r] = __ldg(reinterpret_cast<const float4*>(sparse + (size_t)y * W + x_thr));
-            }
-        }
-        // the neighbours have finished reading the exchange buffers of the previous task (they arrived right after their
-        // step loop): waited for here, where its latency overlaps the loads above, not in front of the step loop
-        if (!first) cluster_wait();
-        // the first row exchange of a task needs only blur_depth: it is published from inside the prologue (below), so its
-        // DSMEM round trip hides under the normalisation instead of stalling the first step
-        const bool early_publish = (MODE != kAdjoint) && !(GENERAL && init != nullptr);
-
-        mbar_wait(bar_tma, ph_tma);
-        ph_tma ^= 1;
-        CSPN_STAMP(xc, 1);
-
-        constexpr int kLag = PR >= 3 ? 2 : 1;
-        float inv[PR][PC];
-#pragma unroll
-        for (int s = 0; s < PR + kLag; ++s) {
-            if (s < PR) {
-                // ---- phase 1 of row s: a_k(y,x) = g_k(y+dy_k, x+dx_k).  dy_k came with the TMA box; dx_k is applied here:
-                // the thread reads its own PC columns of plane k and takes the missing neighbour column from the next /
-                // previous lane (tile edge lanes read the apron column of the staged row instead).  w holds the raw a_k.
-                const int r = s;
-                float S[PC];
-#pragma unroll
-                for (int j = 0; j < PC; ++j) S[j] = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float* row = stage + ((size_t)k * RB + wy * PR + r) * TWP + 4 + lane * PC;
-                    float v[PC], a[PC];
-                    load_row_smem(row, v);
-                    if (off2_dx(k) == 1) {
-                        float nb = __shfl_down_sync(0xffffffffu, v[0], 1);
-                        if (lane == 31) nb = row[PC];
-#pragma unroll
-                        for (int j = 0; j < PC - 1; ++j) a[j] = v[j + 1];
-                        a[PC - 1] = nb;
-                    } else if (off2_dx(k) == -1) {
-                        float nb = __shfl_up_sync(0xffffffffu, v[PC - 1], 1);
-                        if (lane == 0) nb = row[-1];
-#pragma unroll
-                        for (int j = PC - 1; j > 0; --j) a[j] = v[j - 1];
-                        a[0] = nb;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < PC; ++j) a[j] = v[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) {
-                        if (ABS) a[j] = fabsf(a[j]);             // cspn.py:88-89
-                        S[j] += fabsf(a[j]);                      // cspn.py:135-136
-                        w[r][j][k] = a[j];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < PC; ++j) inv[r][j] = rcp_approx(S[j]);
-            }
-            if (s == kLag && early_publish) {
-                const float top[PC] = {dv[0].x, dv[0].y, dv[0].z, dv[0].w};
-                const float bot[PC] = {dv[PR - 1].x, dv[PR - 1].y, dv[PR - 1].z, dv[PR - 1].w};
-                publish<PR, PC, NW, 0>(xc, wy, top, bot);
-            }
-            if (s >= kLag) {
-                // ---- phase 2 of row s - kLag: w'_k = (1-m) a_k / S, c' = (1 - sum_k w'_k) d_0 -----------------------------
-                const int r = s - kLag;
-                const bool in = col_in && (y_thr + r < H);
-                d[r][0] = dv[r].x; d[r][1] = dv[r].y; d[r][2] = dv[r].z; d[r][3] = dv[r].w;
-                const float mm[PC] = {signf(sv[r].x), signf(sv[r].y), signf(sv[r].z), signf(sv[r].w)};
-                float cj[PC];
-                bool exact_div = false;
-#pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    // a * (1/S) is a / S to 2 ulp and has the same 0/0, x/inf and inf/inf results, EXCEPT when 1/S
-                    // overflows (S subnormal): there the reference's quotient (cspn.py:138) is an ordinary number
-                    exact_div |= in && (inv[r][j] > 8.0e37f);
-                }
-                if (exact_div) {                               // cold: IEEE division, the reference's own expression
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) {
-                        float S = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) S += fabsf(w[r][j][k]);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) w[r][j][k] = __fdiv_rn(w[r][j][k], S);
-                        inv[r][j] = 1.f;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < PC; ++j) {
-                    const float scale = in ? (1.f - mm[j]) * inv[r][j] : 0.f;   // outside the image: w = 0, c = 0, d = 0 forever
-                    float sw = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        w[r][j][k] *= scale;
-                        sw += w[r][j][k];
-                    }
-                    // (1-m)(1 - gate_sum) + m  ==  1 - sum_k w'_k: the sum of the QUOTIENTS as cspn.py:139 forms it (a sum
-                    // of the raw affinities times 1/S would turn an overflowing sum into inf * 0 = NaN)
-                    cj[j] = in ? (1.f - sw) * d[r][j] : 0.f;
-                }
-                // only this thread ever reads these values back: no barrier needed
-                if constexpr (MODE != kAdjoint) store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
-                // a pass after the first continues from the previous pass's result; c' above still used d_0
-                if (GENERAL && init != nullptr && in) {
-                    const float4 iv = __ldg(reinterpret_cast<const float4*>(init + (size_t)bc * HW + (size_t)(y_thr + r) * W + x_thr));
-                    d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
-                }
-            }
-        }
-#else
-        // blur / sparse: straight from global (aligned, read once; the previous task prefetched them into L2).
-        // W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
+        // blur / sparse rows of this task were REQUESTED at the end of the previous task (request_rows below): by now they
+        // have landed.  W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
         const bool col_in = (x_thr >= 0) && (x_thr < W);
         float m[PR][PC];
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
-            const int y = y_thr + r;
-            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), sv = dv;
-            if (col_in && y < H) {
-                dv = __ldg(reinterpret_cast<const float4*>(blur + (size_t)y * W + x_thr));
-                if (sparse) sv = __ldg(reinterpret_cast<const float4*>(sparse + (size_t)y * W + x_thr));
-            }
-            d[r][0] = dv.x; d[r][1] = dv.y; d[r][2] = dv.z; d[r][3] = dv.w;
-            m[r][0] = signf(sv.x); m[r][1] = signf(sv.y); m[r][2] = signf(sv.z); m[r][3] = signf(sv.w);
+            d[r][0] = dv[r].x; d[r][1] = dv[r].y; d[r][2] = dv[r].z; d[r][3] = dv[r].w;
+            m[r][0] = signf(sv[r].x); m[r][1] = signf(sv[r].y); m[r][2] = signf(sv[r].z); m[r][3] = signf(sv[r].w);
         }
+        // the neighbours have finished reading the exchange buffers of the previous task (they arrived right after their
+        // step loop) ...
+        if (!first) cluster_wait();
+        // ... so the first row exchange of this task -- it needs only blur_depth -- goes out now and its DSMEM round trip
+        // hides under the normalisation below instead of stalling the first step.  (A continuation pass starts from the
+        // previous pass's result, read further down: it publishes after the prologue.)
+        const bool early_publish = (MODE != kAdjoint) && !(GENERAL && init != nullptr);
+        if (early_publish) publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
 
         mbar_wait(bar_tma, ph_tma);
         ph_tma ^= 1;
@@ -1020,8 +685,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 d[r][0] = iv.x; d[r][1] = iv.y; d[r][2] = iv.z; d[r][3] = iv.w;
             }
         }
-        const bool early_publish = false;
-#endif
         CSPN_STAMP(xc, 2);
         __syncthreads();  // every warp is done with the staging buffer
         CSPN_STAMP(xc, 3);
@@ -1033,44 +696,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 fence_proxy_async();  // generic-proxy reads of `stage` above are ordered before the async-proxy writes
                 issue_stage(next);
             }
-            // its blur / sparse rows: pull the lines into L2 (one lane per 128-byte line of the row segment)
-            const int strip_n = next % prm.n_strips, q_n = next / prm.n_strips;
-            const int bc_n = GENERAL ? q_n / prm.n_bands : q_n;
-            const int yn0 = (GENERAL ? prm.band_y0[q_n % prm.n_bands] : 0) + thr_dy;
-            const int xn = prm.tile_x0[strip_n] + lane * PC;
-            if ((lane * PC) % 32 == 0 && xn < W) {
-                const float* bn = prm.blur + (size_t)bc_n * HW;
-                const float* in = (GENERAL && init) ? init + (size_t)bc_n * HW : nullptr;
-                const float* sn = prm.sparse ? prm.sparse + (size_t)(bc_n / prm.C) * HW : nullptr;
-#pragma unroll
-                for (int r = 0; r < PR; ++r) {
-                    const int y = yn0 + r;
-                    if (y < H) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(bn + (size_t)y * W + xn));
-                        if (sn) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + (size_t)y * W + xn));
-                        if (in) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (size_t)y * W + xn));
-                    }
-                }
-            }
         }
 
         // ---- the N iterations: registers only, one mbarrier wait each ----------------------------------
-#if CSPN_PROLOGUE != 2
-        if (!first) cluster_wait();  // the neighbours have finished reading the exchange buffers of the previous task
-#endif
         first = false;
         CSPN_STAMP(xc, 4);
-#ifndef CSPN_SKEW
-#define CSPN_SKEW 300
-#endif
-        if constexpr (K::kGroups == 2) {
-            // start the lower warp group late by about half a step: the two groups then stay out of phase for the whole
-            // task (nothing pulls them back together: each only waits for rows the other one published long before)
-            if (group == 1) {
-                const long long t0 = clock64();
-                while (clock64() - t0 < CSPN_SKEW) {}
-            }
-        }
         const int iters = prm.iters;
         // kStoreSteps / kAdjoint: every step's result also goes to global memory (useful pixels only); the pass's last
         // step leaves through the epilogue
@@ -1118,13 +748,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 #endif
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
-        for (int r = 0; r < PR; ++r) {
-#if CSPN_STEP >= 2
-            row_edges_raw<PC>(d[r], e[r]);
-#else
-            row_edges<PC>(d[r], e[r], xc.first_lane, xc.last_lane);
-#endif
-        }
+        for (int r = 0; r < PR; ++r) row_edges_raw<PC>(d[r], e[r]);
         float d2[PR][PC], e2[PR][2];    // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(xc.cbuf + r * TW, d2[r]);   // accumulators of the first step start from c'
@@ -1157,8 +781,12 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         }
         }   // MODE != kAdjoint
 
+        // ---- the next task's blur / sparse rows are requested now: the weight registers are dead ----------------------
+        if (next < n_tasks) request_rows(next);
+
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
+        const bool fan_out = MODE == kForward && (prm.n_peer != 0 || prm.out_mc != nullptr);   // fused gather (uniform)
         const int ux0 = prm.ux0[strip], ux1 = prm.ux1[strip];
         const int uy0 = GENERAL ? prm.uy0[band] : 0, uy1 = GENERAL ? prm.uy1[band] : H;   // uy1 <= H
         if (x_thr >= ux0 && x_thr < ux1) {
@@ -1168,13 +796,15 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 if (y >= uy0 && y < uy1) {
                     const float4 v = make_float4(d[r][0], d[r][1], d[r][2], d[r][3]);
                     if constexpr (MODE == kForward) {
-                        const size_t off = (size_t)bc * HW + (size_t)y * W + x_thr;
-                        __stcs(reinterpret_cast<float4*>(prm.out + off), v);
-                        for (int e = 0; e < prm.n_peer; ++e)        // peer GPUs' gather buffers (NVLink stores)
-                            __stcs(reinterpret_cast<float4*>(prm.out_peer[e] + off), v);
-                        if (prm.out_mc)                             // NVLS: one store, replicated by the switch
-                            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(prm.out_mc + off),
-                                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        __stcs(reinterpret_cast<float4*>(out + (size_t)y * W + x_thr), v);
+                        if (fan_out) {
+                            const size_t off = (size_t)bc * HW + (size_t)y * W + x_thr;
+                            for (int e = 0; e < prm.n_peer; ++e)    // peer GPUs' gather buffers (NVLink stores)
+                                __stcs(reinterpret_cast<float4*>(prm.out_peer[e] + off), v);
+                            if (prm.out_mc)                         // NVLS: one store, replicated by the switch
+                                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(prm.out_mc + off),
+                                             "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        }
                     } else {
                         *reinterpret_cast<float4*>(out + (size_t)y * W + x_thr) = v;   // read again by the next pass
                     }
@@ -1577,7 +1207,6 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     prm.C = p.C; prm.H = p.H; prm.W = p.W; prm.gch = p.gch; prm.iters = pp.iters; prm.norm_abs = p.norm_abs;
     prm.n_strips = pp.n_strips;
     prm.n_bands = pp.n_bands;
-    prm.zero = 0;
     prm.trace = g_trace;
     prm.n_peer = sc.n_peer;
     for (int i = 0; i < 7; ++i) prm.out_peer[i] = i < sc.n_peer ? sc.peer[i] : nullptr;
