@@ -299,24 +299,35 @@ def other_configs(dev, peak, sm_max_mhz):
     sets = [[t.to(dev) for t in make_inputs(sd, Bn, 1, Hn, Wn)] for sd in (1, 2)]
     px = Bn * Hn * Wn
     sweep = {}
+    from cspn_b200 import torch_op
+    torch_op.load()
     for n in (4, 8, 16, 24, 48):
-        state = {'i': 0}
-
-        def call():
-            g, d, s = sets[state['i'] & 1]
-            state['i'] += 1
-            return cspn_b200.propagate2d(g, d, s, n, NORM)
-        ms = event_times(call, 10, 3)
-        t = ms[len(ms) // 2] * 1e-3
+        # these calls last 60-350 us: eager launches would be paced by the host (the queue runs dry between calls), so
+        # 10 calls alternating the two input sets are captured into one CUDA graph and the replay is timed
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for g, d, s in sets:
+                torch.ops.cspn_b200.propagate2d(g, d, s, n, 0, 0)
+        torch.cuda.current_stream().wait_stream(side)
+        launches, algo_name = L.cspn_last_launches(), _lib.ALGO_NAMES[L.cspn_last_algo()]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(10):
+                g, d, s = sets[i & 1]
+                torch.ops.cspn_b200.propagate2d(g, d, s, n, 0, 0)
+        ms = event_times(graph.replay, 7, 2)
+        t = ms[len(ms) // 2] * 1e-3 / 10
         rate = px / t
         sweep[str(n)] = {'us': round(t * 1e6, 1), 'mpx_s': round(rate / 1e6, 1),
                          'hbm_gbs': round(ALGO_BYTES_PER_PX * rate / 1e9, 1), 'hbm_frac': round(ALGO_BYTES_PER_PX * rate / 1e9 / peak, 4),
                          'fp32_ceiling_mpx_s': round(fma_peak / (8 * n + 30) / 1e6, 1),
                          'fp32_frac': round(rate / (fma_peak / (8 * n + 30)), 4),
-                         'launches': L.cspn_last_launches(), 'algo': _lib.ALGO_NAMES[L.cspn_last_algo()]}
+                         'launches': launches, 'algo': algo_name}
+        del graph
     out['cfg3_nyu_sweep'] = {'workload': f'2D CSPN 3x3, {NORM}, with sparse depth, batch {Bn}x{Wn}x{Hn} (BASELINE configs[2])',
-                             'timing': 'median of 10 CUDA-event timed calls after 3 warm-up; two input sets alternate '
-                                       '(2 x 195 MB > 126 MB L2)',
+                             'timing': 'one CUDA graph of 10 calls alternating two input sets (2 x 195 MB > 126 MB L2), median of 7 '
+                                       'CUDA-event timed replays after 2 warm-up, per call',
                              'fp32_ceiling': f'148 SM x 128 FMA/clk x {sm_max_mhz} MHz / (8 N + 30) FMA per pixel (BASELINE.md section 2)',
                              'by_iters': sweep}
     del sets

@@ -44,8 +44,11 @@ def _check_inputs_2d(guidance, blur_depth, sparse_depth):
 
 
 def _overlaps(a, b):
-    """True when the storage ranges of two tensors intersect (same device)."""
+    """True when the memory of two tensors intersects.  Different storages (the normal case) are told apart at once; only
+    views of one storage pay for the exact range test."""
     if a is None or b is None or a.device != b.device or a.numel() == 0 or b.numel() == 0:
+        return False
+    if a.untyped_storage().data_ptr() != b.untyped_storage().data_ptr():
         return False
     a0, b0 = a.data_ptr(), b.data_ptr()
     span = lambda t: (sum((n - 1) * abs(st) for n, st in zip(t.shape, t.stride())) + 1) * t.element_size()

@@ -15,13 +15,14 @@
 // The forward iterates d_1..d_{N-1} are recomputed and kept in the workspace ((N-1) B C H W floats).
 //
 // Two formulations:
-//  * launch-per-step (default, validated on B200): generic prep + N-1 forward steps, N adjoint steps that also
-//    read-modify-write the 8 planes of Gw, finalize.  17-30x the cost of the forward (profiles/r01_train_step_timing.txt).
-//  * cluster (STAGED: opt-in with CSPN_B200_BWD=cluster, written after the round's GPU budget was spent and therefore
-//    NOT yet run on hardware): the forward cluster kernel in kStoreSteps mode writes every iterate, the same kernel in
-//    kAdjoint mode runs the transposed stencil register-resident and writes every lambda_t, and one gather kernel forms
+//  * cluster (default; validated on B200 in round 2 against fp64 autograd through the reference's op sequence and the
+//    gradient goldens): the forward cluster kernel in kStoreSteps mode writes every iterate, the same kernel in kAdjoint
+//    mode runs the transposed stencil register-resident and writes every lambda_t, and one gather kernel forms
 //    Gw_k(p) = sum_t lambda_{t+1}(p) d_t(p + off_k), Gc = sum_t lambda_{t+1} straight into the finalize arithmetic:
-//    no Gw planes in memory, 2 N planes of workspace.
+//    no Gw planes in memory, 2 N planes of workspace.  2.6x / 3.2x faster than the next one on the train-step shapes
+//    (profiles/r02_train_step_timing.txt).
+//  * launch-per-step (W % 4 != 0, misaligned tensors, or CSPN_B200_BWD=steps): generic prep + N-1 forward steps, N adjoint
+//    steps that also read-modify-write the 8 planes of Gw, finalize.
 #include <cstdlib>
 #include <cstring>
 
@@ -187,9 +188,11 @@ bwd_gather_finalize_kernel(const float* __restrict__ guidance, const float* __re
         }
 }
 
-bool staged_cluster_backward_requested() {
+// The register-resident formulation is the default; CSPN_B200_BWD=steps forces the launch-per-step one (cross-check in
+// tests/test_cluster_backward_gpu.py, and the path shapes outside the cluster kernel's take anyway).
+bool cluster_backward_enabled() {
     const char* e = getenv("CSPN_B200_BWD");
-    return e && strcmp(e, "cluster") == 0;
+    return !(e && strcmp(e, "steps") == 0);
 }
 
 }  // namespace
@@ -199,11 +202,11 @@ size_t bwd2d_workspace_bytes(int B, int C, int H, int W, int iters) {
     const size_t HW = (size_t)H * W, n = (size_t)B * C * HW;
     // wk (9 planes/image) + d_1..d_{N-1} + lambda ping-pong + Gw + Gc
     const size_t per_step = sizeof(float) * ((size_t)B * 9 * HW + (size_t)(iters - 1) * n + 2 * n + (size_t)B * 8 * HW + n);
-    const size_t cluster = staged_cluster_backward_requested() ? sizeof(float) * 2 * (size_t)iters * n : 0;   // d_1..d_N, lambda_0..lambda_{N-1}
+    const size_t cluster = cluster_backward_enabled() ? sizeof(float) * 2 * (size_t)iters * n : 0;   // d_1..d_N, lambda_0..lambda_{N-1}
     return per_step > cluster ? per_step : cluster;
 }
 
-// Staged cluster formulation (see the file header).  Returns CSPN_ERR_UNSUPPORTED when the shape / alignment is not
+// Cluster formulation (see the file header).  Returns CSPN_ERR_UNSUPPORTED when the shape / alignment is not
 // the cluster kernel's; the caller then falls back to the launch-per-step path.
 static int bwd2d_cluster(const Problem2D& p, const float* grad_out, float* grad_guidance, float* grad_blur, void* ws,
                          cudaStream_t stream, int* launches) {
@@ -241,7 +244,7 @@ int bwd2d(const Problem2D& p, const float* grad_out, float* grad_guidance, float
         return CSPN_ERR_WORKSPACE;
     }
     if (p.B > 65535 || (long)p.B * p.C > 65535) { set_error("backward: B*C exceeds gridDim.z"); return CSPN_ERR_UNSUPPORTED; }
-    if (staged_cluster_backward_requested()) {
+    if (cluster_backward_enabled()) {
         const int rc = bwd2d_cluster(p, grad_out, grad_guidance, grad_blur, ws, stream, launches);
         if (rc != CSPN_ERR_UNSUPPORTED) return rc;
         clear_error();   // shape / alignment outside the cluster kernel's: the launch-per-step path below handles it

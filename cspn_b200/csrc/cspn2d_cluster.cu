@@ -138,6 +138,15 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
                  "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar)
                  : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data in flight
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// pull one box of a tensor into L2 (no shared-memory destination, no barrier): one instruction for a whole tile
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
@@ -451,7 +460,8 @@ __device__ __forceinline__ void iterate_adj(const Xch& x, int wy, uint32_t phase
 // single-band launch (every BASELINE 2D config) pays nothing for them.
 template <int PR, int PC, int NW, bool ABS, bool GENERAL, int MODE = kForward>
 __global__ void __launch_bounds__(32 * NW, 1)
-cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ ClusterParams prm) {
+cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ CUtensorMap tm_blur,
+                      const __grid_constant__ CUtensorMap tm_sparse, const __grid_constant__ ClusterParams prm) {
     using K = Cfg<PR, PC, NW>;
     constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP, TWX = K::TWX;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -535,31 +545,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     }
     cluster_wait();
 
-    // blur / sparse rows of task t, straight from global into registers (aligned float4, read once).  Requested one task
-    // ahead: after the step loop the 160 weight registers are dead, so the 2 x PR float4 in flight cost nothing, and the
-    // latency (HBM: nothing prefetches them) hides behind the epilogue stores, the index arithmetic and the TMA wait.
-    float4 dv[PR], sv[PR];
-    auto request_rows = [&](int t) {
-        const int strip_t = t % prm.n_strips, q_t = t / prm.n_strips;
-        const int bc_t = GENERAL ? q_t / prm.n_bands : q_t;
-        const int y0 = (GENERAL ? prm.band_y0[q_t % prm.n_bands] : 0) + thr_dy;
-        const int x0 = prm.tile_x0[strip_t] + lane * PC;
-        const float* bl = prm.blur + (size_t)bc_t * HW;
-        const float* sp = prm.sparse ? prm.sparse + (size_t)(bc_t / prm.C) * HW : nullptr;
-        const bool cin = (x0 >= 0) && (x0 < W);
-#pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            const int y = y0 + r;
-            dv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            sv[r] = dv[r];
-            if (cin && y < H) {
-                dv[r] = __ldg(reinterpret_cast<const float4*>(bl + (size_t)y * W + x0));
-                if (sp) sv[r] = __ldg(reinterpret_cast<const float4*>(sp + (size_t)y * W + x0));
-            }
-        }
-    };
-    if (task < n_tasks) request_rows(task);
-
     uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
@@ -586,23 +571,32 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         const float* blur = prm.blur + (size_t)bc * HW;
         const float* sparse = prm.sparse ? prm.sparse + (size_t)b * HW : nullptr;
 
-        // blur / sparse rows of this task were REQUESTED at the end of the previous task (request_rows below): by now they
-        // have landed.  W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
+        // blur_depth rows go global -> shared with cp.async, straight into this thread's slots of the c' buffer (free until
+        // the prologue writes c' there): nothing holds them in flight, and the prologue reads each row back when it needs
+        // it.  sparse_depth rows (only their sign is used) wait in registers and are converted row by row.  Both were
+        // pulled into L2 one task ago by the TMA prefetch below, so what is hidden here is an L2 latency.
+        // W % 4 == 0 and x_thr % 4 == 0: a float4 is entirely inside or outside the image.
         const bool col_in = (x_thr >= 0) && (x_thr < W);
-        float m[PR][PC];
+        float4 sv[PR];
+        float* my_c = const_cast<float*>(xc.cbuf);
 #pragma unroll
         for (int r = 0; r < PR; ++r) {
-            d[r][0] = dv[r].x; d[r][1] = dv[r].y; d[r][2] = dv[r].z; d[r][3] = dv[r].w;
-            m[r][0] = signf(sv[r].x); m[r][1] = signf(sv[r].y); m[r][2] = signf(sv[r].z); m[r][3] = signf(sv[r].w);
+            const int y = y_thr + r;
+            sv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_in && y < H) {
+                cp_async16(smem_u32(my_c + r * TW), blur + (size_t)y * W + x_thr);
+                if (sparse) sv[r] = __ldg(reinterpret_cast<const float4*>(sparse + (size_t)y * W + x_thr));
+            } else {
+                *reinterpret_cast<float4*>(my_c + r * TW) = sv[r];       // outside the image: d = 0
+            }
         }
         // the neighbours have finished reading the exchange buffers of the previous task (they arrived right after their
-        // step loop) ...
+        // step loop): waited for here, under the loads
         if (!first) cluster_wait();
-        // ... so the first row exchange of this task -- it needs only blur_depth -- goes out now and its DSMEM round trip
-        // hides under the normalisation below instead of stalling the first step.  (A continuation pass starts from the
-        // previous pass's result, read further down: it publishes after the prologue.)
+        // the first row exchange of a task needs only blur_depth: it is published from inside the prologue (after row 0),
+        // so its DSMEM round trip hides under the normalisation of the other rows instead of stalling the first step.
+        // (A continuation pass starts from the previous pass's result, read further down: it publishes after the prologue.)
         const bool early_publish = (MODE != kAdjoint) && !(GENERAL && init != nullptr);
-        if (early_publish) publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
 
         mbar_wait(bar_tma, ph_tma);
         ph_tma ^= 1;
@@ -646,13 +640,22 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                     A[j] += a[k][j];                           // numerator of gate_sum, cspn.py:139
                 }
             }
+            // this row's blur_depth (from the c' slot the cp.async filled) and mask
+            if (r == 0) cp_async_wait_all();            // this thread's own copies: no barrier needed
+            load_row_smem(my_c + r * TW, d[r]);
+            const float mrow[PC] = {signf(sv[r].x), signf(sv[r].y), signf(sv[r].z), signf(sv[r].w)};
+            if (r == 0 && early_publish) {
+                float bot[PC];
+                load_row_smem(my_c + (PR - 1) * TW, bot);
+                publish<PR, PC, NW, 0>(xc, wy, d[0], bot);
+            }
             float cj[PC];
             bool exact_div = false;
 #pragma unroll
             for (int j = 0; j < PC; ++j) {
                 const bool in = col_in && (y < H);
                 const float inv = rcp_approx(S[j]);
-                const float om = 1.f - m[r][j];
+                const float om = 1.f - mrow[j];
                 const float scale = in ? om * inv : 0.f;      // pixels outside the image: w = 0, c = 0, d = 0 forever
                 float sw = 0.f;
 #pragma unroll
@@ -666,7 +669,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             if (exact_div) {                                   // cold: IEEE division, the reference's own expression
 #pragma unroll
                 for (int j = 0; j < PC; ++j) {
-                    const float om = 1.f - m[r][j];
+                    const float om = 1.f - mrow[j];
                     float gsum = 0.f;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
@@ -674,7 +677,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                         gsum += q;                             // gate_sum, cspn.py:139
                         w[r][j][k] = om * q;
                     }
-                    cj[j] = (om * (1.f - gsum) + m[r][j]) * d[r][j];
+                    cj[j] = (om * (1.f - gsum) + mrow[j]) * d[r][j];
                 }
             }
             // only this thread ever reads these values back: no barrier needed
@@ -695,6 +698,13 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             if (tid == 0) {
                 fence_proxy_async();  // generic-proxy reads of `stage` above are ordered before the async-proxy writes
                 issue_stage(next);
+                // its blur / sparse rows: one TMA prefetch each pulls the CTA's whole tile into L2 (two instructions per CTA
+                // and task; the per-thread prefetch loop this replaces cost 1 250 cycles of every task)
+                const int strip_n = next % prm.n_strips, q_n = next / prm.n_strips;
+                const int bc_n = GENERAL ? q_n / prm.n_bands : q_n;
+                const int y_n = (GENERAL ? prm.band_y0[q_n % prm.n_bands] : 0) + cta_dy;
+                tma_prefetch_3d(&tm_blur, prm.tile_x0[strip_n], y_n, bc_n);
+                if (prm.sparse) tma_prefetch_3d(&tm_sparse, prm.tile_x0[strip_n], y_n, bc_n / prm.C);
             }
         }
 
@@ -780,9 +790,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
         }
         }   // MODE != kAdjoint
-
-        // ---- the next task's blur / sparse rows are requested now: the weight registers are dead ----------------------
-        if (next < n_tasks) request_rows(next);
 
         // ---- epilogue: useful columns straight to global ------------------------------------------------
         float* out = prm.out + (size_t)bc * HW;
@@ -1156,50 +1163,61 @@ int plan_for_launch(const Problem2D& p, Plan& plan) {
 // One pass = one launch of `fn` with plan `pp`.  `start` plays the role of blur_depth (kAdjoint: lambda's start value),
 // `init` continues from an earlier pass (kForward / kStoreSteps), `iter_out` / `iter_stride` say where every step but
 // the last is written (kStoreSteps / kAdjoint), the last step goes to `out`.
+// Tiled 3D tensor map over `planes` row-major (H, W) fp32 planes, box (bx, by, 1).  The descriptor is a pure function of
+// (base pointer, shape, box): serving loops call with the same buffers again and again, so the last few encodings are
+// kept (the driver call costs microseconds, which is what a 1-image problem lasts).
+int tensor_map_3d(const float* base, int W, int H, int planes, int bx, int by, CUtensorMap& tm) {
+    struct MapKey { const void* base; int W, H, planes, bx, by; };
+    struct MapEntry { MapKey key; CUtensorMap tm; };
+    constexpr int kCached = 16;
+    static MapEntry cache[kCached];
+    static int n_cached = 0, next_slot = 0;
+    const MapKey key{base, W, H, planes, bx, by};
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        for (int i = 0; i < n_cached; ++i) {
+            const MapKey& c = cache[i].key;
+            if (c.base == key.base && c.W == key.W && c.H == key.H && c.planes == key.planes && c.bx == key.bx && c.by == key.by) {
+                tm = cache[i].tm;
+                return CSPN_OK;
+            }
+        }
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+    CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, W, H, planes, bx, by);
+        return CSPN_ERR_CUDA;
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    cache[next_slot] = MapEntry{key, tm};
+    next_slot = (next_slot + 1) % kCached;
+    if (n_cached < kCached) ++n_cached;
+    return CSPN_OK;
+}
+
 struct Scatter { float* const* peer = nullptr; int n_peer = 0; float* mc = nullptr; };
 
 int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const float* start, const float* init, float* out,
                 float* iter_out, long long iter_stride, cudaStream_t stream, const Scatter& sc = Scatter()) {
     const KernelCfg& k = configs()[pp.cfg];
-    // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane.  The descriptor is a
-    // pure function of (base pointer, shape, box): serving loops call with the same buffers again and again, so the last
-    // few encodings are kept (the driver call costs microseconds, which is what a 1-image problem lasts).
-    CUtensorMap tm;
-    {
-        struct MapKey { const void* base; int W, H, planes, bx, by; };
-        struct MapEntry { MapKey key; CUtensorMap tm; };
-        static MapEntry cache[8];
-        static int n_cached = 0, next_slot = 0;
-        const MapKey key{p.guidance, p.W, p.H, p.B * p.gch, k.TW() + 8, k.RB()};
-        bool hit = false;
-        {
-            std::lock_guard<std::mutex> lock(g_mu);
-            for (int i = 0; i < n_cached && !hit; ++i) {
-                const MapKey& c = cache[i].key;
-                if (c.base == key.base && c.W == key.W && c.H == key.H && c.planes == key.planes && c.bx == key.bx && c.by == key.by) {
-                    tm = cache[i].tm;
-                    hit = true;
-                }
-            }
-        }
-        if (!hit) {
-            const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.gch};
-            const cuuint64_t strides[2] = {(cuuint64_t)p.W * sizeof(float), (cuuint64_t)p.W * p.H * sizeof(float)};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            const cuuint32_t box[3] = {(cuuint32_t)k.TW() + 8, (cuuint32_t)k.RB(), 1};  // 4 apron columns per side
-            CUresult cr = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.guidance), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (cr != CUDA_SUCCESS) {
-                set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d box=%dx%d)", (int)cr, p.W, p.H,
-                          p.B * p.gch, k.TW(), k.RB());
-                return CSPN_ERR_CUDA;
-            }
-            std::lock_guard<std::mutex> lock(g_mu);
-            cache[next_slot] = MapEntry{key, tm};
-            next_slot = (next_slot + 1) % 8;
-            if (n_cached < 8) ++n_cached;
-        }
+    // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane (4 apron columns per
+    // side).  blur / sparse as (W, H, planes) with (TW, RB, 1) boxes: only ever PREFETCHED into L2 through their maps.
+    CUtensorMap tm, tm_blur, tm_sparse;
+    int rc = tensor_map_3d(p.guidance, p.W, p.H, p.B * p.gch, k.TW() + 8, k.RB(), tm);
+    if (rc != CSPN_OK) return rc;
+    rc = tensor_map_3d(start, p.W, p.H, p.B * p.C, k.TW(), k.RB(), tm_blur);
+    if (rc != CSPN_OK) return rc;
+    if (p.sparse) {
+        rc = tensor_map_3d(p.sparse, p.W, p.H, p.B, k.TW(), k.RB(), tm_sparse);
+        if (rc != CSPN_OK) return rc;
+    } else {
+        tm_sparse = tm_blur;      // never dereferenced (prm.sparse == nullptr)
     }
     ClusterParams prm;
     prm.blur = start; prm.init = init; prm.sparse = p.sparse; prm.out = out;
@@ -1237,7 +1255,7 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    void* args[2] = {(void*)&tm, (void*)&prm};
+    void* args[4] = {(void*)&tm, (void*)&tm_blur, (void*)&tm_sparse, (void*)&prm};
     CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
     return CSPN_OK;
 }
