@@ -247,7 +247,9 @@ class Affinity_Propagate3D(nn.Module):
     (cspn_paddle/demo.py:20-54: CSPN.cspn(guide, feat)).  norm_type:
       '26sum' / '26sum_abs' -- the cspn.py scheme lifted to 3D (gathered affinities, centre term);
       'paddle'              -- demo.py's |guide| / sum_k |guide_k| at the voxel's own location,
-                               then prop_time applications of out = sum_k gate_k * shift_k(feat)."""
+                               then prop_time applications of out = sum_k gate_k * shift_k(feat).
+    guidance is (B,26,D,H,W) -- one gate shared by all C feature channels (cspn_paddle/README.md:56) -- or (B,26*C,D,H,W):
+    one gate per feature channel, demo.py:28-45."""
 
     def __init__(self, prop_time, prop_kernel=3, norm_type='26sum_abs'):
         super().__init__()
@@ -257,6 +259,14 @@ class Affinity_Propagate3D(nn.Module):
         self._use_op = _use_torch_op()
 
     def forward(self, guidance, feat):
+        if feat.dim() == 5 and guidance.dim() == 5 and feat.shape[1] > 1 and guidance.shape[1] == 26 * feat.shape[1]:
+            # per-channel gates, the feat.shape[1] > 1 branch of CSPN.cspn (cspn_paddle/demo.py:28-45): channel c of feat is
+            # propagated with guide channels [26c, 26c+26).  In memory that IS a batch of B*C single-channel volumes with
+            # 26-channel gates, so the views below cost nothing (contiguous inputs) and the same kernels run.
+            B, C = feat.shape[:2]
+            out = self.forward(guidance.contiguous().view(B * C, 26, *guidance.shape[2:]),
+                               feat.contiguous().view(B * C, 1, *feat.shape[2:]))
+            return out.view(feat.shape)
         if self._use_op and feat.is_cuda and self.prop_time > 0:
             return torch.ops.cspn_b200.propagate3d(guidance, feat, self.prop_time, NORM3D[self.norm_type])
         if torch.is_grad_enabled() and (guidance.requires_grad or feat.requires_grad) and self.prop_time > 0:

@@ -135,6 +135,20 @@ CSPN_API int cspn3d_bwd_f32(const float* guidance, const float* feat, const floa
                    int B, int C, int D, int H, int W, int iters, int norm_type,
                    void* workspace, size_t workspace_bytes, cspn_stream_t stream);
 
+/* ---- what the reference does with the result on the HOST after every step, on the device ------------------------
+ * utils.evaluate_error(gt_depth, pred_depth) (cspn_pytorch/utils.py:19-47; called at train.py:206, eval.py:150 after a
+ * `.cpu()` of both tensors) and Wighted_L1_Loss (loss.py:12-23).  One pass over n = B*C*H*W elements; out12 (DEVICE):
+ *   [0] n_valid (gt > 1e-4)  [1] MSE  [2] RMSE  [3] MAE (== the masked L1 loss)  [4] ABS_REL
+ *   [5..10] DELTA1.02, 1.05, 1.10, 1.25, 1.25^2, 1.25^3   [11] reserved (LG10: never filled by the reference)
+ * workspace: cspn_depth_metrics_workspace_bytes() bytes of 8-byte aligned device memory.  Enqueue only, no sync. */
+CSPN_API size_t cspn_depth_metrics_workspace_bytes(void);
+CSPN_API int cspn_depth_metrics_f32(const float* pred, const float* gt, size_t n, float* out12,
+                           void* workspace, size_t workspace_bytes, cspn_stream_t stream);
+/* gradient of the masked L1 loss w.r.t. pred: grad_loss (device scalar, NULL = 1) * sign(pred - gt) / n_valid where
+ * gt > 1e-4, else 0; stats12 is the out12 of cspn_depth_metrics_f32 on the same tensors (autograd through loss.py:16-23) */
+CSPN_API int cspn_masked_l1_bwd_f32(const float* pred, const float* gt, const float* stats12, const float* grad_loss,
+                           float* grad_pred, size_t n, cspn_stream_t stream);
+
 /* ---- pinned host buffers for the *_host entry points ---------------------------------------- */
 CSPN_API void* cspn_host_alloc(size_t bytes); /* cudaHostAlloc; NULL on failure */
 CSPN_API void cspn_host_free(void* p);

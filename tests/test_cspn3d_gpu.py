@@ -84,3 +84,32 @@ def test_3d_gradients_match_autograd_of_the_restatement(shape, n, mode):
         scale = theirs.abs().mean()
         err = (ours - theirs).abs()
         assert (err <= 2e-3 * (theirs.abs() + scale)).all(), (name, mode, float(err.max()), float(scale))
+
+
+@pytest.mark.parametrize('mode', ['paddle', '26sum_abs'])
+def test_3d_per_channel_gates_like_demo_py(mode):
+    """cspn_paddle/demo.py:28-45: with C > 1 feature channels the guide carries 26*C channels and channel c is propagated
+    with its own slice [26c, 26c+26).  Checked against the oracle applied slice by slice, forward and backward."""
+    B, C, D, H, W, n = 2, 3, 5, 8, 12, 4
+    gen = torch.Generator().manual_seed(11)
+    guide = torch.rand(B, 26 * C, D, H, W, generator=gen)
+    feat = torch.rand(B, C, D, H, W, generator=gen)
+    layer = cspn_b200.Affinity_Propagate3D(n, 3, mode)
+    gc, fc = guide.cuda().requires_grad_(True), feat.cuda().requires_grad_(True)
+    out = layer(gc, fc)
+    assert out.shape == feat.shape
+    ref = np.stack([c_oracle.cspn3d(guide[:, 26 * c:26 * (c + 1)].contiguous().numpy(), feat[:, c:c + 1].contiguous().numpy(), n, mode)[:, 0]
+                    for c in range(C)], 1)
+    ok, ratio, normwise = onp.parity_ok(out.detach().cpu().numpy(), ref, 1e-4)
+    assert ok, (ratio, normwise)
+    out.sum().backward()
+    # gradients: the same thing done channel by channel with shared-gate calls
+    gg = torch.zeros_like(guide)
+    gf = torch.zeros_like(feat)
+    for c in range(C):
+        g1 = guide[:, 26 * c:26 * (c + 1)].contiguous().cuda().requires_grad_(True)
+        f1 = feat[:, c:c + 1].contiguous().cuda().requires_grad_(True)
+        layer(g1, f1).sum().backward()
+        gg[:, 26 * c:26 * (c + 1)] = g1.grad.cpu()
+        gf[:, c:c + 1] = f1.grad.cpu()
+    assert torch.allclose(gc.grad.cpu(), gg, rtol=1e-5, atol=1e-7) and torch.allclose(fc.grad.cpu(), gf, rtol=1e-5, atol=1e-7)
