@@ -680,23 +680,6 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                     cj[j] = (om * (1.f - gsum) + mrow[j]) * d[r][j];
                 }
             }
-#ifndef CSPN_NO_BANK_PIN
-            // Register-file banks.  An FFMA with three distinct source registers needs two issue cycles whenever two of them
-            // sit in the same (even / odd) bank and none comes from the operand-reuse cache; the step loop is bound by exactly
-            // that (tools/sass_loop.py: 624 register-file cycles for its 320 FFMAs).  Accumulators are 128-bit quads (they are
-            // seeded by LDS.128), so pixel j's accumulator has parity j.  Storing this row's weights as quads in SWAPPED pixel
-            // order -- {w[1][k], w[0][k], w[3][k], w[2][k]} -- makes ptxas materialise each quad in four consecutive
-            // registers, i.e. pixel j's weight gets parity NOT j: weight and accumulator of every tap are in different
-            // banks by construction, and the tap costs one cycle whenever its value operand is reused.  The store itself
-            // goes to staging words this thread has already consumed (its own 4 columns of row r, plane k) and is never read.
-            {
-                float* dead = stage + ((size_t)(wy * PR + r)) * TWP + 4 + lane * PC;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(dead + (size_t)k * RB * TWP)), "f"(w[r][1][k]),
-                                 "f"(w[r][0][k]), "f"(w[r][3][k]), "f"(w[r][2][k]) : "memory");
-            }
-#endif
             // only this thread ever reads these values back: no barrier needed
             if constexpr (MODE != kAdjoint) store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
             // a pass after the first continues from the previous pass's result; c' above still used d_0
