@@ -132,6 +132,75 @@ step3d_vec4_kernel(const float* __restrict__ wk, const float* __restrict__ d0, c
     *reinterpret_cast<float4*>(dst + (size_t)c * V + p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
+// 'paddle' normalisation straight from the RAW guidance (cspn_paddle/demo.py:24,47-52): the gate of tap k is
+// |g_k(p)| / sum_j |g_j(p)| at the voxel's own location, so one step is  out(p) = (sum_k |g_k(p)| cur(p + off_k)) / (sum_k |g_k(p)|):
+// ONE division per voxel instead of 26, no normalised-weight planes at all (no prep launch, no workspace for weights, 27
+// instead of 29 planes read per step).  0 / 0 = NaN as with explicit gates.  The 26 guidance float4 of a thread are
+// requested back to back before any arithmetic (CSPN3D_HOIST, default on): the kernel lives on loads in flight.
+#ifndef CSPN3D_HOIST
+#define CSPN3D_HOIST 1
+#endif
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+    float4 v;
+#if CSPN3D_HOIST
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#else
+    v = __ldg(reinterpret_cast<const float4*>(p));
+#endif
+    return v;
+}
+
+#ifndef CSPN3D_PADDLE_BLOCKS
+#define CSPN3D_PADDLE_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, CSPN3D_PADDLE_BLOCKS)
+step3d_paddle_vec4_kernel(const float* __restrict__ g, const float* __restrict__ cur, float* __restrict__ dst, int C, int D, int H,
+                          int W) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z % D, c = blockIdx.z / D;   // c = volume * C + channel
+    if (x >= W || y >= H) return;
+    const size_t HW = (size_t)H * W, V = (size_t)D * HW;
+    const size_t p = (size_t)z * HW + (size_t)y * W + x;
+    g += (size_t)(c / C) * 26 * V;
+    const float* cc = cur + (size_t)c * V;
+    float4 w[26];
+#pragma unroll
+    for (int k = 0; k < 26; ++k) w[k] = ld_stream(g + k * V + p);
+    float rows[3][3][6];
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int zz = z + dz, yy = y + dy;
+            float* r = rows[dz + 1][dy + 1];
+            if (zz >= 0 && zz < D && yy >= 0 && yy < H) {
+                const float* src = cc + (size_t)zz * HW + (size_t)yy * W + x;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w;
+                r[0] = x > 0 ? __ldg(src - 1) : 0.f;
+                r[5] = x + 4 < W ? __ldg(src + 4) : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) r[i] = 0.f;
+            }
+        }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 26; ++k) {
+        const float a0 = fabsf(w[k].x), a1 = fabsf(w[k].y), a2 = fabsf(w[k].z), a3 = fabsf(w[k].w);
+        const float* r = rows[off3_dz(k) + 1][off3_dy(k) + 1];
+        const int o = 1 + off3_dx(k);
+        S[0] += a0; S[1] += a1; S[2] += a2; S[3] += a3;
+        acc[0] = fmaf(a0, r[o], acc[0]);
+        acc[1] = fmaf(a1, r[o + 1], acc[1]);
+        acc[2] = fmaf(a2, r[o + 2], acc[2]);
+        acc[3] = fmaf(a3, r[o + 3], acc[3]);
+    }
+    *reinterpret_cast<float4*>(dst + (size_t)c * V + p) =
+        make_float4(__fdiv_rn(acc[0], S[0]), __fdiv_rn(acc[1], S[1]), __fdiv_rn(acc[2], S[2]), __fdiv_rn(acc[3], S[3]));
+}
+
 }  // namespace
 
 // Volumes per launch group: as many as keep the group's workspace under kMaxWorkspace3d (and gridDim.z legal).
@@ -171,6 +240,25 @@ int generic3d_forward(const float* guidance, const float* feat, float* out, int 
     if ((size_t)D * C > 65535 || D > 65535) {
         set_error("3D path: D*C=%zu exceeds gridDim.z", (size_t)D * C);
         return CSPN_ERR_UNSUPPORTED;
+    }
+    const bool vec4_all = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out) |
+                                              reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(guidance)) % 16 == 0);
+    const char* raw_env = getenv("CSPN_B200_3D_PADDLE");     // developer hook: "planes" forces the prep + weight-plane path
+    if (mode == 2 && vec4_all && !(raw_env && raw_env[0] == 'p') && (size_t)D * C * B <= 65535 &&
+        (iters == 1 || ws_bytes >= (size_t)B * C * V * sizeof(float))) {
+        // 'paddle': gates straight from the raw guidance, every volume in one launch per step; the workspace's first
+        // C*B*V floats are the ping-pong buffer
+        float* tmp = static_cast<float*>(ws);
+        const float* cur = feat;
+        float* dst = (iters & 1) ? out : tmp;
+        for (int it = 0; it < iters; ++it) {
+            step3d_paddle_vec4_kernel<<<dim3((W / 4 + 31) / 32, (H + 3) / 4, D * C * B), dim3(32, 4), 0, stream>>>(guidance, cur, dst, C, D, H, W);
+            ++*launches;
+            cur = dst;
+            dst = (dst == out) ? tmp : out;
+        }
+        CSPN_CUDA_TRY(cudaGetLastError());
+        return CSPN_OK;
     }
     const int G = group3d(B, C, D, H, W, iters);
     float* wk = static_cast<float*>(ws);          // [G][27][V]
