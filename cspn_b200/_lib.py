@@ -39,6 +39,7 @@ SIGNATURES = {
     'cspn_last_launches': (_i, []),
     'cspn2d_describe_plan': (_i, [_i] * 6 + [_cp, _i]),
     'cspn2d_plan_json': (_i, [_i] * 3 + [_cp, _i]),
+    'cspn2d_plan_json_chained': (_i, [_i] * 3 + [_cp, _i]),
 }
 
 
@@ -76,9 +77,9 @@ def describe_plan(B, C, H, W, iters, algo=ALGO_AUTO):
     return buf.value.decode()
 
 
-def plan_info(H, W, iters):
-    """The cluster path's plan for an HxW image and `iters` steps as a dict (see cspn2d_plan_json)."""
+def plan_info(H, W, iters, chained=False):
+    """The cluster path's plan for an HxW image and `iters` steps as a dict (see cspn2d_plan_json[_chained])."""
     import json
     buf = ctypes.create_string_buffer(1 << 16)
-    lib().cspn2d_plan_json(H, W, iters, buf, len(buf))
+    (lib().cspn2d_plan_json_chained if chained else lib().cspn2d_plan_json)(H, W, iters, buf, len(buf))
     return json.loads(buf.value.decode())

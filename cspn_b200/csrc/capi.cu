@@ -234,7 +234,13 @@ int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int algo, char* 
 int cspn2d_plan_json(int H, int W, int iters, char* buf, int buf_len) {
     if (!buf || buf_len <= 0) return 0;
     if (H <= 0 || W <= 0 || iters <= 0) return snprintf(buf, buf_len, "{\"supported\": false, \"why\": \"invalid shape\"}");
-    return cluster2d_plan_json(H, W, iters, buf, buf_len);
+    return cluster2d_plan_json(H, W, iters, 0, buf, buf_len);
+}
+
+int cspn2d_plan_json_chained(int H, int W, int iters, char* buf, int buf_len) {
+    if (!buf || buf_len <= 0) return 0;
+    if (H <= 0 || W <= 0 || iters <= 0) return snprintf(buf, buf_len, "{\"supported\": false, \"why\": \"invalid shape\"}");
+    return cluster2d_plan_json(H, W, iters, 1, buf, buf_len);
 }
 
 }  // extern "C"

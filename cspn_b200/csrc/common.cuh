@@ -64,7 +64,7 @@ size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters);
 int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_t stream, int* launches,
                       float* const* peer_out = nullptr, int n_peer = 0, float* mc_out = nullptr);
 int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len);
-int cluster2d_plan_json(int H, int W, int iters, char* buf, int len);
+int cluster2d_plan_json(int H, int W, int iters, int chained, char* buf, int len);
 // staged (opt-in, see cspn2d_bwd.cu): the forward keeping every iterate, and the adjoint sweep, on the cluster kernel
 int cluster2d_forward_steps(const Problem2D& p, float* steps, cudaStream_t stream, int* launches);
 int cluster2d_adjoint_steps(const Problem2D& p, const float* grad_out, float* lam, cudaStream_t stream, int* launches);

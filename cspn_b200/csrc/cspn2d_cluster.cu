@@ -42,6 +42,7 @@ namespace {
 constexpr int kMaxStrips = 128;
 constexpr int kMaxBands = 64;
 constexpr int kMaxPasses = 1024;
+constexpr int kChainMaxIters = 32;    // chained strips: steps per pass whose recorded columns fit the history buffers
 
 struct ClusterParams {
     const float* blur;    // [B*C][H][W]  d_0: the constant term always comes from here (cspn.py:58,76,81)
@@ -59,6 +60,11 @@ struct ClusterParams {
     int n_peer;
     float* out_mc;
     unsigned long long* trace;   // -DCSPN_TRACE builds only (tools/trace_cluster.py): per-warp clock stamps, else null
+    // chained strips (CHAIN kernels): the strips of an image are processed left to right; strip j records the column just left
+    // of strip j+1 at every step (`hist`), so strip j+1 has an exact left neighbour and only its right edge goes stale
+    float* hist;                 // [boundary block][step][warp][8] floats, block = (j * n_tasks / n_strips + q) * cluster size + CTA
+    unsigned* flags;             // one word per block, zeroed before the launch; 1 = the block's history is complete
+    int chain_lane;              // lane whose 4th column is recorded (the column left of the next strip's tile)
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -186,6 +192,12 @@ struct Cfg {
     // iteration (one LDS.128 per patch row), which frees PR*PC registers per thread
     static constexpr size_t kCBytes = (size_t)RB * TW * sizeof(float);
     static constexpr size_t kSmemBytes = kStageBytes + kXchBytes + kCBytes + 64;
+    // chained strips: the recorded column of the left neighbour strip (in) and of this strip (out), [step][warp][8 rows]
+    static constexpr int kChainMaxIters = cspn::kChainMaxIters;
+    static constexpr int kHistRow = NW * 8;
+    static constexpr size_t kHistBytes = (size_t)kChainMaxIters * kHistRow * sizeof(float);
+    static constexpr size_t kSmemBytesChain = kSmemBytes + 2 * kHistBytes;
+    static constexpr bool kChainFits = kSmemBytesChain <= 232448 && PR <= 8;
     static_assert(PC == 4, "vectorised global/shared accesses below assume 4 columns per thread");
     static_assert(TWP <= 256, "TMA box <= 256 columns");
     static_assert(RB <= 256 && RB % 4 == 0, "TMA box rows; plane size must stay a multiple of 128 B");
@@ -251,6 +263,9 @@ struct Xch {
     bool remote_up, remote_dn, sig_tx, sig;
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
+    // chained strips (CHAIN kernels; set per task)
+    bool store_hist;      // this lane owns the recorded column and the strip has a right neighbour strip
+    float* hin;           // this warp's 8 floats of step 0 in the history-in buffer; history-out lies kHistBytes further
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
@@ -315,12 +330,19 @@ __device__ __forceinline__ void row_edges_raw(const float (&v)[PC], float (&ed)[
     ed[1] = __shfl_down_sync(0xffffffffu, v[0], 1);
 }
 
-template <int PR, int PC, int NW, int PAR, bool PUBLISH>
+// CHAIN (chained strips).  A history row holds, for one step t and one warp, the recorded column at time t: [0..3] the warp's
+// rows 0..3, [4] the row above its patch, [5] the row below, [6] its row 4.  `hrow` = this warp's slot of row t of the step
+// being taken.  The lane that owns the recorded column stores row t after the wait (it then holds all seven values: its
+// input rows and the two halo rows); lane 0 reads its halo rows' column -1 from row t instead of the zero pad (a pointer
+// select: no extra load) and, at the end of the step, the column -1 of its own rows for the next step from row t+1.  A strip
+// without a left neighbour reads a zero-filled history: the reference's zero padding, so the left taps of lane 0 are never
+// predicated off in these kernels.
+template <int PR, int PC, int NW, int PAR, bool PUBLISH, bool CHAIN = false>
 __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                          float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
-                                         float (&eout)[PR][2]) {
+                                         float (&eout)[PR][2], float* hrow = nullptr) {
     using K = Cfg<PR, PC, NW>;
-    const bool ul = !x.first_lane, ur = !x.last_lane;
+    const bool ul = CHAIN ? true : !x.first_lane, ur = !x.last_lane;
     // ---- A: own-row taps of the two boundary rows ----------------------------------------------------------------
     scatter_row2<PC, 0, true>(w[0], Row<PC>{din[0], ein[0]}, dout[0], ul, ur);
     scatter_row2<PC, +1, true>(w[0], Row<PC>{din[1], ein[1]}, dout[0], ul, ur);
@@ -339,8 +361,22 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         float u[PC], ue[2], d[PC], de[2];
         load_row_smem(pu, u);
         load_row_smem(pd, d);
-        ue[0] = pu[-1]; ue[1] = pu[PC];                   // pad floats are zero at the tile edges
-        de[0] = pd[-1]; de[1] = pd[PC];
+        if constexpr (CHAIN) {
+            ue[0] = *(x.first_lane ? hrow + 4 : pu - 1);
+            de[0] = *(x.first_lane ? hrow + 5 : pd - 1);
+            if (x.store_hist) {
+                float* q = hrow + K::kHistBytes / sizeof(float);      // history-out
+                *reinterpret_cast<float4*>(q) = make_float4(din[0][PC - 1], din[1][PC - 1], din[PR > 2 ? 2 : 0][PC - 1], din[PR > 3 ? 3 : 0][PC - 1]);
+                q[4] = u[PC - 1];
+                q[5] = d[PC - 1];
+                if constexpr (PR > 4) q[6] = din[PR > 4 ? 4 : 0][PC - 1];
+            }
+        } else {
+            ue[0] = pu[-1];                               // pad floats are zero at the tile edges
+            de[0] = pd[-1];
+        }
+        ue[1] = pu[PC];
+        de[1] = pd[PC];
         scatter_row2<PC, -1, false>(w[0], Row<PC>{u, ue}, dout[0], true, true);
         scatter_row2<PC, +1, false>(w[PR - 1], Row<PC>{d, de}, dout[PR - 1], true, true);
     }
@@ -363,17 +399,150 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         scatter_row2<PC, +1, true>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r], ul, ur);
         if constexpr (PUBLISH) row_edges_raw<PC>(dout[r], eout[r]);
     }
+    if constexpr (CHAIN && PUBLISH) {   // column -1 of my rows at the next step (row t+1 of the history)
+        const float* hn = hrow + K::kHistRow;
+        const float4 h = *reinterpret_cast<const float4*>(hn);
+        eout[0][0] = x.first_lane ? h.x : eout[0][0];
+        eout[1][0] = x.first_lane ? h.y : eout[1][0];
+        if constexpr (PR > 2) eout[2][0] = x.first_lane ? h.z : eout[2][0];
+        if constexpr (PR > 3) eout[3][0] = x.first_lane ? h.w : eout[3][0];
+        if constexpr (PR > 4) eout[4][0] = x.first_lane ? hn[6] : eout[4][0];
+        static_assert(PR <= 5, "a history row has room for five patch rows");
+    }
     if constexpr (PUBLISH) {   // seeds of the next step's boundary rows, into the now dead input set
         load_row_smem(x.cbuf, din[0]);
         load_row_smem(x.cbuf + (PR - 1) * K::TW, din[PR - 1]);
     }
 }
 
-template <int PR, int PC, int NW, int PAR, bool PUBLISH>
+// ---- the same step on FFMA2 (fma.rn.f32x2) ----------------------------------------------------------------------------
+// An FFMA reads three distinct registers over two register-file banks: two issue cycles each (profiles/r02_tuning_log.md).
+// fma.rn.f32x2 does two IEEE FMAs on 64-bit register pairs at one instruction per two cycles: the same pipe time for half
+// the instructions and no bank stalls -- provided every operand already IS an aligned register pair.  A thread's four
+// columns c0..c3 are therefore held as the STRIDED pairs S0 = (c0, c2) and S1 = (c1, c3).  A tap with dx = +-1 maps pairs
+// onto pairs: S0 reads (c-1, c1) =: T- , S0, S1 for dx = -1, 0, +1 and S1 reads S0, S1, (c2, c4) =: T+ ; T- and T+ cost one
+// shuffle (or one LDS.32 of the padded exchange row) plus one MOV each per source row.  Shared-memory rows that only this
+// kernel reads (c', exchange rows) keep every quad in the order (c0, c2, c1, c3), so an LDS.128 / STS.128 / st.async moves
+// two pairs; columns -1 and 4 of a quad are still the floats next to it.  Tile-edge lanes zero the shuffled-in half (a
+// select; half an FFMA2 cannot be predicated): the reference's zero padding, taken literally.
+// Everything that lives across steps is a 64-bit value (P2) so that the register allocator sees pairs, not two floats it
+// may place apart (with float2 it kept the rows in the quad order of the loads in front of the loop and rebuilt every
+// pair with two MOVs: 186 MOVs per two steps).
+typedef unsigned long long P2;
+__device__ __forceinline__ P2 pk(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float p_lo(P2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float p_hi(P2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ P2 ffma2(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+struct RowP {
+    const P2 (&v)[2];
+    const P2 (&ed)[2];
+    __device__ __forceinline__ P2 operator()(int u) const { return u < 0 ? ed[0] : (u >= 2 ? ed[1] : v[u]); }
+};
+__device__ __forceinline__ void load_row_smem_p(const float* p, P2 (&v)[2]) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(smem_u32(p)) : "memory");
+}
+// source pair u = q + dx feeds destination pair q; source-major order as in scatter_row2
+template <int SRC_DY, typename Src>
+__device__ __forceinline__ void scatter_row_p(const P2 (&w)[2][8], const Src& src, P2 (&acc)[2]) {
+#pragma unroll
+    for (int ux = 0; ux <= 3; ++ux) {
+        const int su = ux <= 1 ? ux : (ux == 2 ? -1 : 2);
+        const P2 xv = src(su);
+#pragma unroll
+        for (int dx = 1; dx >= -1; --dx) {
+            const int q = su - dx;
+            if (q < 0 || q >= 2) continue;
+            if (SRC_DY == 0 && dx == 0) continue;
+            acc[q] = ffma2(w[q][tap_of(SRC_DY, dx)], xv, acc[q]);
+        }
+    }
+}
+__device__ __forceinline__ void row_edges_p(const P2 (&v)[2], P2 (&ed)[2], bool first_lane, bool last_lane) {
+    const float l = __shfl_up_sync(0xffffffffu, p_hi(v[1]), 1);      // c3 of the lane to the left  = my column -1
+    const float r = __shfl_down_sync(0xffffffffu, p_lo(v[0]), 1);    // c0 of the lane to the right = my column 4
+    ed[0] = pk(first_lane ? 0.f : l, p_lo(v[1]));                    // T- = (c-1, c1)
+    ed[1] = pk(p_hi(v[0]), last_lane ? 0.f : r);                     // T+ = (c2, c4)
+}
+// publish() for rows held as pairs
+template <int PR, int NW, int PAR>
+__device__ __forceinline__ void publish_p(const Xch& x, int wy, const P2 (&top)[2], const P2 (&bot)[2]) {
+    using K = Cfg<PR, 4, NW>;
+    // (two 64-bit stores per row instead of one 128-bit store do not save the four MOVs that gather a row's two pairs into
+    // an aligned register quad: ptxas fuses them back into an STS.128)
+    const uint32_t p = smem_u32(x.base + (size_t)PAR * K::kSlots * K::TWX);
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(p + (uint32_t)((1 + 2 * wy) * K::TWX * 4)), "l"(top[0]), "l"(top[1]) : "memory");
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(p + (uint32_t)((2 + 2 * wy) * K::TWX * 4)), "l"(bot[0]), "l"(bot[1]) : "memory");
+    const uint32_t bar = x.bar_full0 + 8 * PAR;
+    if (x.remote_up)
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(
+                         x.up_data + PAR * (uint32_t)K::kXchParityBytes), "l"(top[0]), "l"(top[1]), "r"(x.up_bar + 8 * PAR) : "memory");
+    if (x.remote_dn)
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(
+                         x.dn_data + PAR * (uint32_t)K::kXchParityBytes), "l"(bot[0]), "l"(bot[1]), "r"(x.dn_bar + 8 * PAR) : "memory");
+    __syncwarp();
+    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
+    mbar_arrive_if(bar, x.sig);
+}
+
+// Same phases as iterate3: A own-row taps of the boundary rows, B wait -> halo taps -> publish, C interior rows (seeded
+// with c' after the publish, which pins the order), D seeds of the next step's boundary rows.
+template <int PR, int NW, int PAR, bool PUBLISH>
+__device__ __forceinline__ void iterate_p(Xch& x, int wy, uint32_t phase, const P2 (&w)[PR][2][8], P2 (&din)[PR][2],
+                                          const P2 (&ein)[PR][2], P2 (&dout)[PR][2], P2 (&eout)[PR][2]) {
+    using K = Cfg<PR, 4, NW>;
+    scatter_row_p<0>(w[0], RowP{din[0], ein[0]}, dout[0]);
+    scatter_row_p<+1>(w[0], RowP{din[1], ein[1]}, dout[0]);
+    scatter_row_p<0>(w[PR - 1], RowP{din[PR - 1], ein[PR - 1]}, dout[PR - 1]);
+    scatter_row_p<-1>(w[PR - 1], RowP{din[PR - 2], ein[PR - 2]}, dout[PR - 1]);
+#ifndef CSPN_ABLATE_NO_SYNC
+    CSPN_STAMP(x, 5 + 3 * x.step);
+    mbar_wait(x.bar_full0 + 8 * PAR, phase);
+    CSPN_STAMP(x, 6 + 3 * x.step);
+#endif
+    {
+        const float* p = x.base + (size_t)PAR * K::kSlots * K::TWX;
+        const float* pu = p + (2 * wy) * K::TWX;          // row above my patch
+        const float* pd = p + (2 * wy + 3) * K::TWX;      // row below my patch
+        P2 u[2], ue[2], d[2], de[2];
+        load_row_smem_p(pu, u);
+        load_row_smem_p(pd, d);
+        ue[0] = pk(pu[-1], p_lo(u[1])); ue[1] = pk(p_hi(u[0]), pu[4]);   // pad floats are zero at the tile edges
+        de[0] = pk(pd[-1], p_lo(d[1])); de[1] = pk(p_hi(d[0]), pd[4]);
+        scatter_row_p<-1>(w[0], RowP{u, ue}, dout[0]);
+        scatter_row_p<+1>(w[PR - 1], RowP{d, de}, dout[PR - 1]);
+    }
+    if constexpr (PUBLISH) {
+#ifndef CSPN_ABLATE_NO_SYNC
+        publish_p<PR, NW, PAR ^ 1>(x, wy, dout[0], dout[PR - 1]);
+        CSPN_STAMP(x, 7 + 3 * x.step);
+#else
+        asm volatile("" ::: "memory");
+#endif
+        row_edges_p(dout[0], eout[0], x.first_lane, x.last_lane);
+        row_edges_p(dout[PR - 1], eout[PR - 1], x.first_lane, x.last_lane);
+    }
+#pragma unroll
+    for (int r = 1; r + 1 < PR; ++r) {
+        load_row_smem_p(x.cbuf + r * K::TW, dout[r]);
+        scatter_row_p<-1>(w[r], RowP{din[r - 1], ein[r - 1]}, dout[r]);
+        scatter_row_p<0>(w[r], RowP{din[r], ein[r]}, dout[r]);
+        scatter_row_p<+1>(w[r], RowP{din[r + 1], ein[r + 1]}, dout[r]);
+        if constexpr (PUBLISH) row_edges_p(dout[r], eout[r], x.first_lane, x.last_lane);
+    }
+    if constexpr (PUBLISH) {
+        load_row_smem_p(x.cbuf, din[0]);
+        load_row_smem_p(x.cbuf + (PR - 1) * K::TW, din[PR - 1]);
+    }
+#ifdef CSPN_TRACE
+    ++x.step;
+#endif
+}
+
+template <int PR, int PC, int NW, int PAR, bool PUBLISH, bool CHAIN = false>
 __device__ __forceinline__ void step_fwd(Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                          float (&din)[PR][PC], float (&ein)[PR][2], float (&dout)[PR][PC],
-                                         float (&eout)[PR][2]) {
-    iterate3<PR, PC, NW, PAR, PUBLISH>(x, wy, phase, w, din, ein, dout, eout);
+                                         float (&eout)[PR][2], float* hrow = nullptr) {
+    iterate3<PR, PC, NW, PAR, PUBLISH, CHAIN>(x, wy, phase, w, din, ein, dout, eout, hrow);
 #ifdef CSPN_TRACE
     ++x.step;
 #endif
@@ -458,18 +627,28 @@ __device__ __forceinline__ void iterate_adj(const Xch& x, int wy, uint32_t phase
 
 // GENERAL = false compiles out row bands and the continuation input of multi-pass plans: the common single-pass,
 // single-band launch (every BASELINE 2D config) pays nothing for them.
-template <int PR, int PC, int NW, bool ABS, bool GENERAL, int MODE = kForward>
+template <int PR, int PC, int NW, bool ABS, bool GENERAL, int MODE = kForward, bool CHAIN = false>
 __global__ void __launch_bounds__(32 * NW, 1)
 cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __grid_constant__ CUtensorMap tm_blur,
                       const __grid_constant__ CUtensorMap tm_sparse, const __grid_constant__ ClusterParams prm) {
     using K = Cfg<PR, PC, NW>;
     constexpr int RB = K::RB, TW = K::TW, TWP = K::TWP, TWX = K::TWX;
+    // -DCSPN_PAIRS: the forward step on FFMA2 with strided column pairs (iterate_p); shared-memory rows are then kept in the
+    // quad order (c0, c2, c1, c3).  Measured 410 us against 404 us for the scalar step on cfg2 (profiles/r02_tuning_log.md):
+    // an FFMA2 with three distinct register pairs occupies the issue port for three cycles (profiles/r02_rfprobe.txt).
+#ifdef CSPN_PAIRS
+    constexpr bool kPairs = (MODE == kForward) && !CHAIN;
+#else
+    constexpr bool kPairs = false;
+#endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     float* xch = reinterpret_cast<float*>(smem_raw + K::kStageBytes);
     float* cbuf = reinterpret_cast<float*>(smem_raw + K::kStageBytes + K::kXchBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::kStageBytes + K::kXchBytes + K::kCBytes);
     const uint32_t bar_tma = smem_u32(bars), bar_full0 = smem_u32(bars + 1);
+    [[maybe_unused]] float* hist_in = reinterpret_cast<float*>(smem_raw + K::kSmemBytes);   // CHAIN: [step][warp][8], then history-out
+    static_assert(!CHAIN || (MODE == kForward && K::kChainFits), "chained strips: forward kernels of the 8-warp configurations");
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int wy = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, provably warp-uniform for the compiler
@@ -500,6 +679,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
+    xc.store_hist = false; xc.hin = nullptr;
+    if constexpr (CHAIN) xc.hin = hist_in + wy * 8;
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -509,8 +690,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     // Stage the 8 guidance planes of one task: rows shifted by dy_k ride on the box origin; out-of-image rows and
     // columns arrive as zeros (= ZeroPad2d, cspn.py:105-129).
     auto issue_stage = [&](int t) {
-        const int strip_t = t % prm.n_strips;
-        const int q_t = t / prm.n_strips;
+        // task order: strips of one image are neighbours (default), or strip-major when the strips are chained (a task's
+        // left neighbour strip is then n_tasks / n_strips tasks back: finished long before, whatever cluster ran it)
+        const int nq_t = prm.n_tasks / prm.n_strips;
+        const int strip_t = CHAIN ? t / nq_t : t % prm.n_strips;
+        const int q_t = CHAIN ? t % nq_t : t / prm.n_strips;
         const int band_t = GENERAL ? q_t % prm.n_bands : 0;
         const int b_t = (GENERAL ? q_t / prm.n_bands : q_t) / prm.C;
         mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
@@ -548,9 +732,11 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     uint32_t ph_tma = 0, ph0 = 0, ph1 = 0;  // phase parities of the three mbarriers (they run on across tasks)
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
-        const int strip = task % prm.n_strips;
-        const int band = GENERAL ? (task / prm.n_strips) % prm.n_bands : 0;
-        const int bc = GENERAL ? (task / prm.n_strips) / prm.n_bands : task / prm.n_strips;  // b*C + c
+        const int nq = prm.n_tasks / prm.n_strips;
+        const int strip = CHAIN ? task / nq : task % prm.n_strips;
+        const int qi = CHAIN ? task % nq : task / prm.n_strips;      // image-channel (x band)
+        const int band = GENERAL ? qi % prm.n_bands : 0;
+        const int bc = GENERAL ? qi / prm.n_bands : qi;  // b*C + c
         const int b = bc / prm.C;
         const int y_thr = (GENERAL ? prm.band_y0[band] : 0) + thr_dy;   // first image row of this thread
         const float* init = GENERAL ? prm.init : nullptr;
@@ -565,6 +751,17 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         }
         CSPN_STAMP(xc, 0);
 #endif
+
+        // chained strip with a left neighbour: ask for that strip's "history complete" flag now, look at the answer after the
+        // loads below have been issued (it was set long ago unless the batch is small)
+        [[maybe_unused]] unsigned hist_ready = 1u;
+        [[maybe_unused]] const unsigned* hist_flag = nullptr;
+        if constexpr (CHAIN) {
+            if (strip > 0) {
+                hist_flag = prm.flags + ((size_t)(strip - 1) * nq + qi) * csize + crank;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(hist_ready) : "l"(hist_flag) : "memory");
+            }
+        }
 
         // ---- thread state ---------------------------------------------------------------------------
         float w[PR][PC][8], d[PR][PC];
@@ -593,6 +790,25 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         // the neighbours have finished reading the exchange buffers of the previous task (they arrived right after their
         // step loop): waited for here, under the loads
         if (!first) cluster_wait();
+        [[maybe_unused]] bool has_out = false;
+        if constexpr (CHAIN) {
+            const bool has_in = strip > 0;
+            has_out = strip + 1 < prm.n_strips;
+            xc.store_hist = has_out && lane == prm.chain_lane;
+            if (!has_in) {      // image border on the left: column -1 is the reference's zero padding
+                const int n16 = prm.iters * K::kHistRow / 4;
+                for (int i = tid; i < n16; i += K::kThreads) reinterpret_cast<float4*>(hist_in)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                // the left neighbour strip's history block of this CTA's rows must be complete (normally it has been for a
+                // long time); then pull it into shared memory: it is first read after the prologue's barrier
+                const size_t blk = ((size_t)(strip - 1) * nq + qi) * csize + crank;
+                while (hist_ready == 0u)
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(hist_ready) : "l"(hist_flag) : "memory");
+                const int n16 = prm.iters * K::kHistRow / 4;
+                const float* src = prm.hist + blk * (size_t)(prm.iters * K::kHistRow);
+                for (int i = tid; i < n16; i += K::kThreads) cp_async16(smem_u32(hist_in + 4 * i), src + 4 * i);
+            }
+        }
         // the first row exchange of a task needs only blur_depth: it is published from inside the prologue (after row 0),
         // so its DSMEM round trip hides under the normalisation of the other rows instead of stalling the first step.
         // (A continuation pass starts from the previous pass's result, read further down: it publishes after the prologue.)
@@ -647,7 +863,12 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
             if (r == 0 && early_publish) {
                 float bot[PC];
                 load_row_smem(my_c + (PR - 1) * TW, bot);
-                publish<PR, PC, NW, 0>(xc, wy, d[0], bot);
+                if constexpr (kPairs) {
+                    const float tp[PC] = {d[0][0], d[0][2], d[0][1], d[0][3]}, bp[PC] = {bot[0], bot[2], bot[1], bot[3]};
+                    publish<PR, PC, NW, 0>(xc, wy, tp, bp);
+                } else {
+                    publish<PR, PC, NW, 0>(xc, wy, d[0], bot);
+                }
             }
             float cj[PC];
             bool exact_div = false;
@@ -681,7 +902,12 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 }
             }
             // only this thread ever reads these values back: no barrier needed
-            if constexpr (MODE != kAdjoint) store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
+            if constexpr (kPairs) {
+                const float cp[PC] = {cj[0], cj[2], cj[1], cj[3]};
+                store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cp);
+            } else if constexpr (MODE != kAdjoint) {
+                store_row_smem(const_cast<float*>(xc.cbuf) + r * TW, cj);   // the adjoint has no constant term
+            }
             // a pass after the first continues from the previous pass's result; c' above still used d_0
             if (GENERAL && init != nullptr && col_in && y < H) {
                 const float4 iv = __ldg(reinterpret_cast<const float4*>(init + (size_t)bc * HW + (size_t)y * W + x_thr));
@@ -700,7 +926,7 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 issue_stage(next);
                 // its blur / sparse rows: one TMA prefetch each pulls the CTA's whole tile into L2 (two instructions per CTA
                 // and task; the per-thread prefetch loop this replaces cost 1 250 cycles of every task)
-                const int strip_n = next % prm.n_strips, q_n = next / prm.n_strips;
+                const int strip_n = CHAIN ? next / nq : next % prm.n_strips, q_n = CHAIN ? next % nq : next / prm.n_strips;
                 const int bc_n = GENERAL ? q_n / prm.n_bands : q_n;
                 const int y_n = (GENERAL ? prm.band_y0[q_n % prm.n_bands] : 0) + cta_dy;
                 tma_prefetch_3d(&tm_blur, prm.tile_x0[strip_n], y_n, bc_n);
@@ -752,6 +978,49 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                     for (int j = 0; j < PC; ++j) d[r][j] = d2[r][j];
             }
             cluster_arrive_relaxed();
+        } else if constexpr (kPairs) {
+        // FFMA2 formulation: the same loop on register pairs (see iterate_p)
+        P2 wp[PR][2][8], dp[PR][2], ep[PR][2], dp2[PR][2], ep2[PR][2];
+#pragma unroll
+        for (int r = 0; r < PR; ++r)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                dp[r][q] = pk(d[r][q], d[r][q + 2]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wp[r][q][k] = pk(w[r][q][k], w[r][q + 2][k]);
+            }
+#ifndef CSPN_ABLATE_NO_SYNC
+        if (!early_publish) publish_p<PR, NW, 0>(xc, wy, dp[0], dp[PR - 1]);
+#endif
+#pragma unroll
+        for (int r = 0; r < PR; ++r) row_edges_p(dp[r], ep[r], xc.first_lane, xc.last_lane);
+#pragma unroll
+        for (int r = 0; r < PR; ++r) load_row_smem_p(xc.cbuf + r * TW, dp2[r]);   // accumulators of the first step start from c'
+        int it = 0;
+        for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
+            iterate_p<PR, NW, 0, true>(xc, wy, ph0, wp, dp, ep, dp2, ep2);
+            ph0 ^= 1;
+            iterate_p<PR, NW, 1, true>(xc, wy, ph1, wp, dp2, ep2, dp, ep);
+            ph1 ^= 1;
+        }
+        if (iters - it == 2) {              // the last step of a task has nobody to publish to
+            iterate_p<PR, NW, 0, true>(xc, wy, ph0, wp, dp, ep, dp2, ep2);
+            ph0 ^= 1;
+            iterate_p<PR, NW, 1, false>(xc, wy, ph1, wp, dp2, ep2, dp, ep);
+            ph1 ^= 1;
+        } else if (iters - it == 1) {
+            iterate_p<PR, NW, 0, false>(xc, wy, ph0, wp, dp, ep, dp2, ep2);
+            ph0 ^= 1;
+        }
+        CSPN_STAMP(xc, kTraceEvents - 2);
+        cluster_arrive_relaxed();  // this CTA no longer reads its exchange buffers
+#pragma unroll
+        for (int r = 0; r < PR; ++r)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const P2 v = (iters & 1) ? dp2[r][q] : dp[r][q];
+                d[r][q] = p_lo(v); d[r][q + 2] = p_hi(v);
+            }
         } else {
 #ifndef CSPN_ABLATE_NO_SYNC
         if (!early_publish) publish<PR, PC, NW, 0>(xc, wy, d[0], d[PR - 1]);
@@ -759,26 +1028,30 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         float e[PR][2];                 // x-edges (left, right neighbour) of the rows of d
 #pragma unroll
         for (int r = 0; r < PR; ++r) row_edges_raw<PC>(d[r], e[r]);
+        if constexpr (CHAIN) {          // column -1 of lane 0's rows at step 0 (row 0 of the history)
+#pragma unroll
+            for (int r = 0; r < PR; ++r) e[r][0] = xc.first_lane ? xc.hin[r < 4 ? r : 6] : e[r][0];
+        }
         float d2[PR][PC], e2[PR][2];    // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(xc.cbuf + r * TW, d2[r]);   // accumulators of the first step start from c'
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
-            step_fwd<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            step_fwd<PR, PC, NW, 0, true, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * K::kHistRow);
             ph0 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d2);
-            step_fwd<PR, PC, NW, 1, true>(xc, wy, ph1, w, d2, e2, d, e);
+            step_fwd<PR, PC, NW, 1, true, CHAIN>(xc, wy, ph1, w, d2, e2, d, e, xc.hin + (it + 1) * K::kHistRow);
             ph1 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d);
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
-            step_fwd<PR, PC, NW, 0, true>(xc, wy, ph0, w, d, e, d2, e2);
+            step_fwd<PR, PC, NW, 0, true, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * K::kHistRow);
             ph0 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d2);
-            step_fwd<PR, PC, NW, 1, false>(xc, wy, ph1, w, d2, e2, d, e);
+            step_fwd<PR, PC, NW, 1, false, CHAIN>(xc, wy, ph1, w, d2, e2, d, e, xc.hin + (it + 1) * K::kHistRow);
             ph1 ^= 1;
         } else if (iters - it == 1) {
-            step_fwd<PR, PC, NW, 0, false>(xc, wy, ph0, w, d, e, d2, e2);
+            step_fwd<PR, PC, NW, 0, false, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * K::kHistRow);
             ph0 ^= 1;
         }
         CSPN_STAMP(xc, kTraceEvents - 2);
@@ -818,6 +1091,19 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 }
             }
         }
+        if constexpr (CHAIN) {
+            if (has_out) {      // uniform over the cluster: hand this CTA's rows of the recorded column to the next strip
+                __syncthreads();                                  // every warp's history stores are in shared memory
+                const size_t blk = ((size_t)strip * nq + qi) * csize + crank;
+                float4* dst = reinterpret_cast<float4*>(prm.hist + blk * (size_t)(prm.iters * K::kHistRow));
+                const float4* src = reinterpret_cast<const float4*>(hist_in + K::kHistBytes / sizeof(float));
+                const int n16 = prm.iters * K::kHistRow / 4;
+                for (int i = tid; i < n16; i += K::kThreads) __stcg(dst + i, src[i]);
+                __syncthreads();
+                // release is cumulative over what the barrier made visible to this thread: no separate fence
+                if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prm.flags + blk), "r"(1u) : "memory");
+            }
+        }
         CSPN_STAMP(xc, kTraceEvents - 1);
     }
     // No CTA may exit while a neighbour could still address its shared memory.
@@ -831,7 +1117,8 @@ struct KernelCfg {
     const void* fn[2][2];      // kForward: [general][norm_abs]
     const void* fn_steps[2];   // kStoreSteps [norm_abs]
     const void* fn_adj[2];     // kAdjoint    [norm_abs]
-    size_t smem;
+    const void* fn_chain[2][2];   // kForward with chained strips: [general][norm_abs]; null when the configuration has no such kernel
+    size_t smem, smem_chain;
     int RB() const { return PR * NW; }
     int TW() const { return 32 * PC; }
 };
@@ -845,16 +1132,27 @@ KernelCfg make_cfg() {
                       (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true, kStoreSteps>},
                      {(const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, true, kAdjoint>,
                       (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true, kAdjoint>},
-                     Cfg<PR, PC, NW>::kSmemBytes};
+                     {{nullptr, nullptr}, {nullptr, nullptr}},
+                     Cfg<PR, PC, NW>::kSmemBytes, 0};
+}
+template <int PR, int PC, int NW>
+KernelCfg make_cfg_chain() {
+    KernelCfg k = make_cfg<PR, PC, NW>();
+    k.fn_chain[0][0] = (const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, false, kForward, true>;
+    k.fn_chain[0][1] = (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, false, kForward, true>;
+    k.fn_chain[1][0] = (const void*)&cspn2d_cluster_kernel<PR, PC, NW, false, true, kForward, true>;
+    k.fn_chain[1][1] = (const void*)&cspn2d_cluster_kernel<PR, PC, NW, true, true, kForward, true>;
+    k.smem_chain = Cfg<PR, PC, NW>::kSmemBytesChain;
+    return k;
 }
 
 // The menu the planner picks from.  Register budget per pixel: 8 weights + value + second value set (c' is in shared
 // memory); 8 warps (2 per SM sub-partition) may use 255 registers each -> up to 20 pixels per thread.
 const std::vector<KernelCfg>& configs() {
     static const std::vector<KernelCfg> v = {
-        make_cfg<5, 4, 8>(),   // 40 rows x 128 cols, 20 px/thread
-        make_cfg<4, 4, 8>(),   // 32 x 128
-        make_cfg<3, 4, 8>(),   // 24 x 128
+        make_cfg_chain<5, 4, 8>(),   // 40 rows x 128 cols, 20 px/thread
+        make_cfg_chain<4, 4, 8>(),   // 32 x 128
+        make_cfg_chain<3, 4, 8>(),   // 24 x 128
         make_cfg<2, 4, 8>(),   // 16 x 128 (small images)
         make_cfg<5, 4, 4>(),   // 20 x 128 with 4 warps: two CTAs (of different tasks) fit one SM and de-phase each other
     };
@@ -864,6 +1162,8 @@ const std::vector<KernelCfg>& configs() {
 // One pass = one launch that advances every image by `iters` steps.
 struct PassPlan {
     int cfg = -1, cs = 0, iters = 0, max_clusters = 0;
+    bool chained = false;     // strips are processed left to right and hand their boundary column on (one-sided halos)
+    int chain_lane = 0;
     int n_strips = 0, n_bands = 0;
     int tile_x0[kMaxStrips], ux0[kMaxStrips], ux1[kMaxStrips];
     int band_y0[kMaxBands], uy0[kMaxBands], uy1[kMaxBands];
@@ -881,7 +1181,7 @@ struct Plan {
 
 std::mutex g_mu;
 unsigned long long* g_trace = nullptr;   // -DCSPN_TRACE builds: set through cspn_debug_set_trace
-struct OccKey { int cfg, cs, dev; };
+struct OccKey { int cfg, cs, dev, chained; };
 std::vector<std::pair<OccKey, int>> g_occ_cache;
 bool g_attr_set[16][16] = {};
 
@@ -896,24 +1196,29 @@ int sm_count(int dev) {
 }
 
 // how many clusters of `cs` CTAs of configuration `ci` can be co-resident on the device
-int max_active_clusters(int ci, int cs, int dev) {
+int max_active_clusters(int ci, int cs, int dev, bool chained = false) {
     for (auto& e : g_occ_cache)
-        if (e.first.cfg == ci && e.first.cs == cs && e.first.dev == dev) return e.second;
+        if (e.first.cfg == ci && e.first.cs == cs && e.first.dev == dev && e.first.chained == (int)chained) return e.second;
     const KernelCfg& k = configs()[ci];
+    if (chained && !k.fn_chain[0][0]) return 0;
     if (!g_attr_set[dev & 15][ci]) {
-        const void* all[8] = {k.fn[0][0], k.fn[0][1], k.fn[1][0], k.fn[1][1], k.fn_steps[0], k.fn_steps[1], k.fn_adj[0], k.fn_adj[1]};
-        for (const void* f : all)
-            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem) != cudaSuccess ||
+        const void* all[12] = {k.fn[0][0], k.fn[0][1], k.fn[1][0], k.fn[1][1], k.fn_steps[0], k.fn_steps[1], k.fn_adj[0], k.fn_adj[1],
+                               k.fn_chain[0][0], k.fn_chain[0][1], k.fn_chain[1][0], k.fn_chain[1][1]};
+        for (int i = 0; i < 12; ++i) {
+            const void* f = all[i];
+            if (!f) continue;
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(i >= 8 ? k.smem_chain : k.smem)) != cudaSuccess ||
                 cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
                 cudaGetLastError();
                 return 0;
             }
+        }
         g_attr_set[dev & 15][ci] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs * 64);
     cfg.blockDim = dim3(32 * k.NW);
-    cfg.dynamicSmemBytes = k.smem;
+    cfg.dynamicSmemBytes = chained ? k.smem_chain : k.smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs;
@@ -922,9 +1227,27 @@ int max_active_clusters(int ci, int cs, int dev) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k.fn[1][0], &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    g_occ_cache.push_back({OccKey{ci, cs, dev}, n});
+    if (cudaOccupancyMaxActiveClusters(&n, chained ? k.fn_chain[1][0] : k.fn[1][0], &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    g_occ_cache.push_back({OccKey{ci, cs, dev, (int)chained}, n});
     return n;
+}
+
+// Chained cover of [0, L): tile i starts where tile i-1's useful range ends (its left neighbour column is handed over step
+// by step), so only the RIGHT `halo` positions of a tile go stale; the last tile reaches the image border.
+bool layout_1d_chained(int L, int T, int halo, int align, int min_useful, int max_n, int& n, int* t0, int* u0, int* u1) {
+    n = 0;
+    if (T >= L) return false;                                  // one tile: nothing to chain
+    const int h = (halo + align - 1) / align * align;
+    if (T - h < min_useful) return false;
+    int u = 0;
+    while (u < L) {
+        if (n == max_n) return false;
+        const int e = (u + T >= L) ? L : u + T - h;
+        t0[n] = u; u0[n] = u; u1[n] = e;
+        ++n;
+        u = e;
+    }
+    return true;
 }
 
 // Cover [0, L) with tiles of T positions whose outer `halo` positions (rounded up to `align`) go stale during a pass:
@@ -951,7 +1274,7 @@ bool layout_1d(int L, int T, int halo, int align, int min_useful, int max_n, int
 // Deliberately independent of B and C, so the same image gets the same tiling (hence bit-identical results) whatever
 // batch it is part of.  `dev` < 0: no device query (planning on a CPU-only box): assume the B200 occupancy table
 // measured by tools/probe.
-bool plan_pass(int H, int W, int iters, int dev, int forced, PassPlan& best) {
+bool plan_pass(int H, int W, int iters, int dev, int forced, bool chained, PassPlan& best) {
     static const int kProbe256[17] = {0, 148, 74, 45, 33, 26, 22, 15, 15, 15, 11, 7, 7, 7, 7, 7, 7};
     const char* fcs = getenv("CSPN_B200_FORCE_CS");   // developer hook for tuning runs (with CSPN_B200_FORCE_PASSES)
     const int forced_cs = fcs ? atoi(fcs) : 0;
@@ -963,14 +1286,20 @@ bool plan_pass(int H, int W, int iters, int dev, int forced, PassPlan& best) {
         const KernelCfg& k = cf[ci];
         PassPlan p;
         // columns: 4-aligned strip origins (TMA / float4), at least 16 useful columns per strip
-        if (!layout_1d(W, k.TW(), iters, 4, 16, kMaxStrips, p.n_strips, p.tile_x0, p.ux0, p.ux1)) continue;
+        if (chained) {
+            if (!k.fn_chain[0][0] || iters > kChainMaxIters) continue;
+            if (!layout_1d_chained(W, k.TW(), iters, 4, 16, kMaxStrips, p.n_strips, p.tile_x0, p.ux0, p.ux1)) continue;
+            p.chained = true;
+            p.chain_lane = (k.TW() - (iters + 3) / 4 * 4) / 4 - 1;   // its 4th column is the one left of the next tile
+        } else if (!layout_1d(W, k.TW(), iters, 4, 16, kMaxStrips, p.n_strips, p.tile_x0, p.ux0, p.ux1)) continue;
         const int cs_full = (H + k.RB() - 1) / k.RB();   // cluster height that needs no row halo
         for (int cs = 1; cs <= 16 && cs <= cs_full; ++cs) {
             if (forced_cs > 0 && cs != forced_cs) continue;
             // rows: one band when the cluster spans the image, else overlapping bands (images taller than 16 CTAs,
             // or a cluster size that fills the GPCs better)
             if (!layout_1d(H, cs * k.RB(), iters, 1, 8, kMaxBands, p.n_bands, p.band_y0, p.uy0, p.uy1)) continue;
-            const int mac = dev >= 0 ? max_active_clusters(ci, cs, dev) : kProbe256[cs];
+            if (chained && p.n_bands > 1) continue;     // the recorded column is handed over per CTA row range: one band
+            const int mac = dev >= 0 ? max_active_clusters(ci, cs, dev, chained) : kProbe256[cs];
             if (mac <= 0) continue;
             // tasks x per-task work / co-resident clusters.  Per-task work: 8 FMA per pixel and step plus a fixed part
             // (load, normalisation, store) worth ~15 steps (fit of the cfg3 sweep, profiles/r01_all_configs_timing.txt).
@@ -980,6 +1309,8 @@ bool plan_pass(int H, int W, int iters, int dev, int forced, PassPlan& best) {
             // row bands re-load their halo rows and multiply the task count; measured 7 % slower than this model says
             // on cfg3 at N=4 (profiles/r01_plan_sweep.txt), so a banded plan has to win by a margin
             if (p.n_bands > 1) p.cost *= 1.15;
+            // a chained task is measured ~18 % longer (recorded column: loads, selects, predicated stores per step; hand-over)
+            if (chained) p.cost *= 1.20;
             p.cfg = ci; p.cs = cs; p.max_clusters = mac; p.iters = iters;
             if (best.cfg < 0 || p.cost < best.cost) best = p;
         }
@@ -987,11 +1318,11 @@ bool plan_pass(int H, int W, int iters, int dev, int forced, PassPlan& best) {
     return best.cfg >= 0;
 }
 
-struct PlanKey { int H, W, iters, dev, forced; };
+struct PlanKey { int H, W, iters, dev, forced, chained; };
 std::vector<std::pair<PlanKey, Plan>> g_plan_cache;   // guarded by g_mu; a handful of shapes per process
 
 // Picks the number of passes and each pass's tiling.  Caller holds g_mu.
-bool make_plan(int H, int W, int iters, int dev, Plan& out, char* why, int why_len) {
+bool make_plan(int H, int W, int iters, int dev, Plan& out, char* why, int why_len, bool chained = false) {
     if (W % 4 != 0) { snprintf(why, why_len, "W=%d is not a multiple of 4 (TMA row pitch / vector stores)", W); return false; }
     // developer hook for tuning runs: CSPN_B200_FORCE_CFG=<index into configs()>, CSPN_B200_FORCE_PASSES=<n>
     const char* force = getenv("CSPN_B200_FORCE_CFG");
@@ -1001,7 +1332,7 @@ bool make_plan(int H, int W, int iters, int dev, Plan& out, char* why, int why_l
     const int forced_passes = fpass ? atoi(fpass) : 0;
     for (auto& e : g_plan_cache)
         if (e.first.H == H && e.first.W == W && e.first.iters == iters && e.first.dev == dev && e.first.forced == forced &&
-            !no_cache) { out = e.second; return true; }
+            e.first.chained == (int)chained && !no_cache) { out = e.second; return true; }
     Plan best;
     best.n_pass = 0;
     const int max_pass = iters < kMaxPasses ? iters : kMaxPasses;
@@ -1011,8 +1342,8 @@ bool make_plan(int H, int W, int iters, int dev, Plan& out, char* why, int why_l
         c.n_pass = P;
         c.n_long = iters % P;
         const int a = iters / P;
-        if (!plan_pass(H, W, a, dev, forced, c.shortp)) continue;
-        if (c.n_long > 0 && !plan_pass(H, W, a + 1, dev, forced, c.longp)) continue;
+        if (!plan_pass(H, W, a, dev, forced, chained, c.shortp)) continue;
+        if (c.n_long > 0 && !plan_pass(H, W, a + 1, dev, forced, chained, c.longp)) continue;
         c.cost = (P - c.n_long) * c.shortp.cost + (c.n_long > 0 ? c.n_long * c.longp.cost : 0.0);
         if (best.n_pass == 0 || c.cost < best.cost) best = c;
         // more passes only pay while the halo shrinks faster than the fixed per-task part grows
@@ -1024,7 +1355,7 @@ bool make_plan(int H, int W, int iters, int dev, Plan& out, char* why, int why_l
     }
     if (!no_cache) {
         if (g_plan_cache.size() >= 64) g_plan_cache.erase(g_plan_cache.begin());
-        g_plan_cache.push_back({PlanKey{H, W, iters, dev, forced}, best});
+        g_plan_cache.push_back({PlanKey{H, W, iters, dev, forced, (int)chained}, best});
     }
     out = best;
     return true;
@@ -1086,8 +1417,42 @@ bool cluster2d_supported(const Problem2D& p, char* why, int why_len) {
     return true;
 }
 
+namespace {
+// Chained strips need, per pass, one history block per (strip boundary, image-channel, CTA of the cluster) and a flag each.
+struct ChainWs { size_t hist_bytes = 0, flag_bytes = 0; size_t total() const { return hist_bytes + flag_bytes; } };
+ChainWs chain_ws(const Plan& plan, long BC) {
+    ChainWs w;
+    for (int i = 0; i < 2; ++i) {
+        const PassPlan& pp = i ? plan.shortp : plan.longp;
+        if (pp.cfg < 0 || !pp.chained || (i == 0 && plan.n_long == 0)) continue;
+        const size_t blocks = (size_t)(pp.n_strips - 1) * BC * pp.cs;
+        const size_t hb = (blocks * pp.iters * configs()[pp.cfg].NW * 8 * sizeof(float) + 255) / 256 * 256;
+        const size_t fb = (blocks * sizeof(unsigned) + 255) / 256 * 256;
+        if (hb > w.hist_bytes) w.hist_bytes = hb;
+        if (fb > w.flag_bytes) w.flag_bytes = fb;
+    }
+    return w;
+}
+// The plan a call with B*C image-channels uses when it is given enough workspace: chained strips pay when every cluster
+// has at least two rounds of tasks (a task's left neighbour strip is then long finished) and the planner's model says so.
+// CSPN_B200_CHAIN=0 never chains, =1 chains whenever a chained plan exists (tests, tuning).  Caller holds g_mu.
+bool choose_plan(int H, int W, int iters, int dev, long BC, Plan& plan, bool& chained, char* why, int why_len) {
+    chained = false;
+    if (!make_plan(H, W, iters, dev, plan, why, why_len)) return false;
+    const char* ce = getenv("CSPN_B200_CHAIN");
+    if (ce && ce[0] == '0') return true;
+    Plan cp;
+    char why2[200] = "";
+    if (!make_plan(H, W, iters, dev, cp, why2, sizeof(why2), true)) return true;
+    const bool forced = ce && ce[0] == '1';
+    if (forced || (BC >= 2L * cp.shortp.max_clusters && cp.cost < plan.cost)) { plan = cp; chained = true; }
+    return true;
+}
+}  // namespace
+
 // Passes after the first read the previous pass's result: one extra d-sized buffer (passes alternate between it and
-// `out`, ending in `out`).
+// `out`, ending in `out`).  Chained strips add their history blocks and flags; a call that gets less workspace than that
+// (but enough for the passes) runs the unchained plan.
 size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters) {
     if (iters <= 0) return 0;
     const int dev = current_device_or_none();
@@ -1095,7 +1460,15 @@ size_t cluster2d_workspace_bytes(int B, int C, int H, int W, int iters) {
     Plan plan;
     char why[200] = "";
     if (!make_plan(H, W, iters, dev, plan, why, sizeof(why))) return 0;
-    return plan.n_pass > 1 ? (size_t)B * C * H * W * sizeof(float) : 0;
+    const size_t d_bytes = (size_t)B * C * H * W * sizeof(float);
+    size_t need = plan.n_pass > 1 ? d_bytes : 0;
+    Plan cp;
+    bool chained = false;
+    if (choose_plan(H, W, iters, dev, (long)B * C, cp, chained, why, sizeof(why)) && chained) {
+        const size_t c = (cp.n_pass > 1 ? d_bytes : 0) + chain_ws(cp, (long)B * C).total();
+        if (c > need) need = c;
+    }
+    return need;
 }
 
 int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len) {
@@ -1103,7 +1476,8 @@ int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len
     std::lock_guard<std::mutex> lock(g_mu);
     Plan plan;
     char why[200] = "";
-    if (!make_plan(H, W, iters, dev, plan, why, sizeof(why))) return snprintf(buf, len, "cluster: unsupported (%s)", why);
+    bool chained = false;
+    if (!choose_plan(H, W, iters, dev, (long)B * C, plan, chained, why, sizeof(why))) return snprintf(buf, len, "cluster: unsupported (%s)", why);
     const PassPlan& pp = plan.shortp;
     const KernelCfg& k = configs()[pp.cfg];
     long useful_x = 0, useful_y = 0;
@@ -1115,20 +1489,21 @@ int cluster2d_describe(int B, int C, int H, int W, int iters, char* buf, int len
                  plan.n_pass - plan.n_long, pp.iters);
     return snprintf(buf, len,
                     "cluster: %spatch %dx%d px/thread, %d warps -> CTA tile %d rows x %d cols, cluster of %d CTAs (%d rows), "
-                    "%d strip(s) x %d band(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
-                    passes, k.PR, k.PC, k.NW, k.RB(), k.TW(), pp.cs, pp.cs * k.RB(), pp.n_strips, pp.n_bands,
+                    "%d %sstrip(s) x %d band(s)/image, %ld tasks, %d co-resident clusters, lane efficiency %.2f, smem %zu B",
+                    passes, k.PR, k.PC, k.NW, k.RB(), k.TW(), pp.cs, pp.cs * k.RB(), pp.n_strips, chained ? "chained " : "", pp.n_bands,
                     (long)B * C * pp.n_strips * pp.n_bands, pp.max_clusters,
-                    (double)useful_x * useful_y / ((double)pp.n_strips * k.TW() * pp.n_bands * pp.cs * k.RB()), k.smem);
+                    (double)useful_x * useful_y / ((double)pp.n_strips * k.TW() * pp.n_bands * pp.cs * k.RB()),
+                    chained ? k.smem_chain : k.smem);
 }
 
 // Machine-readable plan (tests/test_plan_cpu.py replays it on the CPU oracle): every pass with its tile geometry.
-int cluster2d_plan_json(int H, int W, int iters, char* buf, int len) {
+int cluster2d_plan_json(int H, int W, int iters, int chained, char* buf, int len) {
     const int dev = current_device_or_none();
     std::lock_guard<std::mutex> lock(g_mu);
     Plan plan;
     char why[200] = "";
-    if (!make_plan(H, W, iters, dev, plan, why, sizeof(why))) return snprintf(buf, len, "{\"supported\": false, \"why\": \"%s\"}", why);
-    int n = snprintf(buf, len, "{\"supported\": true, \"passes\": [");
+    if (!make_plan(H, W, iters, dev, plan, why, sizeof(why), chained != 0)) return snprintf(buf, len, "{\"supported\": false, \"why\": \"%s\"}", why);
+    int n = snprintf(buf, len, "{\"supported\": true, \"chained\": %s, \"passes\": [", chained ? "true" : "false");
     for (int part = 0; part < 2; ++part) {
         const int count = part == 0 ? plan.n_long : plan.n_pass - plan.n_long;
         if (count == 0) continue;
@@ -1202,10 +1577,13 @@ int tensor_map_3d(const float* base, int W, int H, int planes, int bx, int by, C
 }
 
 struct Scatter { float* const* peer = nullptr; int n_peer = 0; float* mc = nullptr; };
+struct ChainBuf { float* hist = nullptr; unsigned* flags = nullptr; size_t flag_bytes = 0; };   // chained passes only
 
 int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const float* start, const float* init, float* out,
-                float* iter_out, long long iter_stride, cudaStream_t stream, const Scatter& sc = Scatter()) {
+                float* iter_out, long long iter_stride, cudaStream_t stream, const Scatter& sc = Scatter(),
+                const ChainBuf& cb = ChainBuf()) {
     const KernelCfg& k = configs()[pp.cfg];
+    const bool chained = cb.hist != nullptr;
     // guidance as a 3D tensor (W, H, B*gch); one box = (TW + 8, RB, 1) floats of one channel plane (4 apron columns per
     // side).  blur / sparse as (W, H, planes) with (TW, RB, 1) boxes: only ever PREFETCHED into L2 through their maps.
     CUtensorMap tm, tm_blur, tm_sparse;
@@ -1226,6 +1604,7 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     prm.n_strips = pp.n_strips;
     prm.n_bands = pp.n_bands;
     prm.trace = g_trace;
+    prm.hist = cb.hist; prm.flags = cb.flags; prm.chain_lane = pp.chain_lane;
     prm.n_peer = sc.n_peer;
     for (int i = 0; i < 7; ++i) prm.out_peer[i] = i < sc.n_peer ? sc.peer[i] : nullptr;
     prm.out_mc = sc.mc;
@@ -1246,15 +1625,23 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * pp.cs));
     cfg.blockDim = dim3(32 * k.NW);
-    cfg.dynamicSmemBytes = k.smem;
+    cfg.dynamicSmemBytes = chained ? k.smem_chain : k.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = pp.cs;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
+    if (chained) {
+        // a task spins on the flag of its left neighbour strip, which another cluster sets: every cluster of the grid must be
+        // resident (the grid is sized by the occupancy query; a cooperative launch makes that a guarantee, not a hope)
+        at[1].id = cudaLaunchAttributeCooperative;
+        at[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+        CSPN_CUDA_TRY(cudaMemsetAsync(cb.flags, 0, cb.flag_bytes, stream));
+    }
     void* args[4] = {(void*)&tm, (void*)&tm_blur, (void*)&tm_sparse, (void*)&prm};
     CSPN_CUDA_TRY(cudaLaunchKernelExC(&cfg, fn, args));
     return CSPN_OK;
@@ -1268,6 +1655,26 @@ int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_
     int rc = plan_for_launch(p, plan);
     if (rc != CSPN_OK) return rc;
     const size_t d_bytes = (size_t)p.B * p.C * p.H * p.W * sizeof(float);
+    // chained strips when the planner wants them and the caller's workspace holds their history blocks
+    ChainBuf cb;
+    {
+        int dev = 0;
+        CSPN_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(g_mu);
+        Plan cp;
+        bool chained = false;
+        char why[200] = "";
+        if (choose_plan(p.H, p.W, p.iters, dev, (long)p.B * p.C, cp, chained, why, sizeof(why)) && chained) {
+            const ChainWs cw = chain_ws(cp, (long)p.B * p.C);
+            const size_t base = cp.n_pass > 1 ? d_bytes : 0;
+            if (ws && ws_bytes >= base + cw.total() && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && d_bytes % 16 == 0) {
+                plan = cp;
+                cb.hist = reinterpret_cast<float*>(static_cast<char*>(ws) + base);
+                cb.flags = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + base + cw.hist_bytes);
+                cb.flag_bytes = cw.flag_bytes;
+            }
+        }
+    }
     if (plan.n_pass > 1 && (!ws || ws_bytes < d_bytes)) {
         set_error("cluster path splits %d steps into %d passes and needs %zu workspace bytes, got %zu", p.iters, plan.n_pass,
                   d_bytes, ws ? ws_bytes : (size_t)0);
@@ -1281,7 +1688,9 @@ int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_
         const bool general = pp.n_bands > 1 || prev != nullptr;
         Scatter sc;
         if (ip == plan.n_pass - 1) { sc.peer = peer_out; sc.n_peer = n_peer; sc.mc = mc_out; }   // only the final result travels
-        rc = launch_pass(p, pp, configs()[pp.cfg].fn[general ? 1 : 0][p.norm_abs ? 1 : 0], p.blur, prev, dst, nullptr, 0, stream, sc);
+        const KernelCfg& kc = configs()[pp.cfg];
+        rc = launch_pass(p, pp, (pp.chained ? kc.fn_chain : kc.fn)[general ? 1 : 0][p.norm_abs ? 1 : 0], p.blur, prev, dst, nullptr, 0, stream, sc,
+                         pp.chained ? cb : ChainBuf());
         if (rc != CSPN_OK) return rc;
         ++*launches;
         prev = dst;

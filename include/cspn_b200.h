@@ -164,6 +164,11 @@ CSPN_API int cspn2d_describe_plan(int B, int C, int H, int W, int iters, int alg
  * row bands [band_y0, uy0, uy1]; {"supported": false, ...} when the shape goes to the generic path.  Returns the
  * bytes needed (output is truncated to buf_len). */
 CSPN_API int cspn2d_plan_json(int H, int W, int iters, char* buf, int buf_len);
+/* The same for the CHAINED plan: the strips of an image are processed left to right and every strip hands the column left
+ * of its right neighbour on, step by step, so only a strip's right edge goes stale (fewer, more useful strips).  The
+ * forward uses it for large batches when the caller's workspace holds cspn2d_workspace_bytes(); "supported": false when
+ * the shape has no such plan (one strip, row bands, more than 32 steps per pass). */
+CSPN_API int cspn2d_plan_json_chained(int H, int W, int iters, char* buf, int buf_len);
 
 #ifdef __cplusplus
 }
