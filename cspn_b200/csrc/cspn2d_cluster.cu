@@ -65,6 +65,9 @@ struct ClusterParams {
     float* hist;                 // [boundary block][step][warp][8] floats, block = (j * n_tasks / n_strips + q) * cluster size + CTA
     unsigned* flags;             // one word per block, zeroed before the launch; 1 = the block's history is complete
     int chain_lane;              // lane whose 4th column is recorded (the column left of the next strip's tile)
+    int chain_group;             // image-channels per task group: tasks run group by group, strip-major inside a group, so that strip
+                                 // j+1 of an image follows strip j by one group size: far enough for strip j to be finished, close
+                                 // enough for the guidance columns the two tiles share to still be in L2 (the last group takes the rest)
     int tile_x0[kMaxStrips];  // column of the strip's first tile column (multiple of 4, may exceed image on the right)
     int ux0[kMaxStrips];      // useful (stored) columns [ux0, ux1)
     int ux1[kMaxStrips];
@@ -391,6 +394,38 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         row_edges_raw<PC>(dout[PR - 1], eout[PR - 1]);
     }
     // ---- C: interior rows (their seed is loaded after the publish: see above) ---------------------------------------------
+#if defined(CSPN_STEP_SRCMAJOR)
+    // experiment: source-major over ALL interior destination rows: the (up to 8) FMAs that consume one source value adjacent
+#pragma unroll
+    for (int r = 1; r + 1 < PR; ++r) load_row_smem(x.cbuf + r * K::TW, dout[r]);
+#pragma unroll
+    for (int sr = 0; sr < PR; ++sr) {
+        const Row<PC> src{din[sr], ein[sr]};
+#pragma unroll
+        for (int jx = 0; jx <= PC + 1; ++jx) {
+            const int sx = jx <= PC - 1 ? jx : (jx == PC ? -1 : PC);
+            const float xv = src(sx);
+#pragma unroll
+            for (int dy = 1; dy >= -1; --dy) {       // source row sr lies dy rows below destination row sr - dy
+                const int r = sr - dy;
+                if (r < 1 || r > PR - 2) continue;
+#pragma unroll
+                for (int dx = 1; dx >= -1; --dx) {
+                    const int j = sx - dx;
+                    if (j < 0 || j >= PC) continue;
+                    if (dy == 0 && dx == 0) continue;
+                    if (sx < 0) { if (ul) dout[r][j] = fmaf(w[r][j][tap_of(dy, dx)], xv, dout[r][j]); }
+                    else if (sx >= PC) { if (ur) dout[r][j] = fmaf(w[r][j][tap_of(dy, dx)], xv, dout[r][j]); }
+                    else dout[r][j] = fmaf(w[r][j][tap_of(dy, dx)], xv, dout[r][j]);
+                }
+            }
+        }
+    }
+    if constexpr (PUBLISH) {
+#pragma unroll
+        for (int r = 1; r + 1 < PR; ++r) row_edges_raw<PC>(dout[r], eout[r]);
+    }
+#else
 #pragma unroll
     for (int r = 1; r + 1 < PR; ++r) {
         load_row_smem(x.cbuf + r * K::TW, dout[r]);
@@ -399,6 +434,7 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         scatter_row2<PC, +1, true>(w[r], Row<PC>{din[r + 1], ein[r + 1]}, dout[r], ul, ur);
         if constexpr (PUBLISH) row_edges_raw<PC>(dout[r], eout[r]);
     }
+#endif
     if constexpr (CHAIN && PUBLISH) {   // column -1 of my rows at the next step (row t+1 of the history)
         const float* hn = hrow + K::kHistRow;
         const float4 h = *reinterpret_cast<const float4*>(hn);
@@ -689,12 +725,23 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
 
     // Stage the 8 guidance planes of one task: rows shifted by dy_k ride on the box origin; out-of-image rows and
     // columns arrive as zeros (= ZeroPad2d, cspn.py:105-129).
+    // CHAIN task order: groups of prm.chain_group image-channels, strip-major inside a group
+    [[maybe_unused]] auto chain_decode = [&](int t, int& strip_o, int& q_o) {
+        const int nq_all = prm.n_tasks / prm.n_strips, g = prm.chain_group;
+        const int per_group = g * prm.n_strips;
+        int grp = t / per_group;
+        const int n_groups = nq_all / g;                 // >= 1; the last group also holds the remainder
+        if (grp >= n_groups) grp = n_groups - 1;
+        const int t2 = t - grp * per_group;
+        const int size = (grp == n_groups - 1) ? nq_all - grp * g : g;
+        strip_o = t2 / size;
+        q_o = grp * g + t2 % size;
+    };
     auto issue_stage = [&](int t) {
         // task order: strips of one image are neighbours (default), or strip-major when the strips are chained (a task's
         // left neighbour strip is then n_tasks / n_strips tasks back: finished long before, whatever cluster ran it)
-        const int nq_t = prm.n_tasks / prm.n_strips;
-        const int strip_t = CHAIN ? t / nq_t : t % prm.n_strips;
-        const int q_t = CHAIN ? t % nq_t : t / prm.n_strips;
+        int strip_t = t % prm.n_strips, q_t = t / prm.n_strips;
+        if constexpr (CHAIN) chain_decode(t, strip_t, q_t);
         const int band_t = GENERAL ? q_t % prm.n_bands : 0;
         const int b_t = (GENERAL ? q_t / prm.n_bands : q_t) / prm.C;
         mbar_arrive_expect_tx(bar_tma, (uint32_t)K::kStageBytes);
@@ -733,8 +780,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     bool first = true;
     for (; task < n_tasks; task += task_stride) {
         const int nq = prm.n_tasks / prm.n_strips;
-        const int strip = CHAIN ? task / nq : task % prm.n_strips;
-        const int qi = CHAIN ? task % nq : task / prm.n_strips;      // image-channel (x band)
+        int strip = task % prm.n_strips, qi = task / prm.n_strips;      // qi: image-channel (x band)
+        if constexpr (CHAIN) chain_decode(task, strip, qi);
         const int band = GENERAL ? qi % prm.n_bands : 0;
         const int bc = GENERAL ? qi / prm.n_bands : qi;  // b*C + c
         const int b = bc / prm.C;
@@ -926,7 +973,8 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
                 issue_stage(next);
                 // its blur / sparse rows: one TMA prefetch each pulls the CTA's whole tile into L2 (two instructions per CTA
                 // and task; the per-thread prefetch loop this replaces cost 1 250 cycles of every task)
-                const int strip_n = CHAIN ? next / nq : next % prm.n_strips, q_n = CHAIN ? next % nq : next / prm.n_strips;
+                int strip_n = next % prm.n_strips, q_n = next / prm.n_strips;
+                if constexpr (CHAIN) chain_decode(next, strip_n, q_n);
                 const int bc_n = GENERAL ? q_n / prm.n_bands : q_n;
                 const int y_n = (GENERAL ? prm.band_y0[q_n % prm.n_bands] : 0) + cta_dy;
                 tma_prefetch_3d(&tm_blur, prm.tile_x0[strip_n], y_n, bc_n);
@@ -1148,6 +1196,19 @@ KernelCfg make_cfg_chain() {
 
 // The menu the planner picks from.  Register budget per pixel: 8 weights + value + second value set (c' is in shared
 // memory); 8 warps (2 per SM sub-partition) may use 255 registers each -> up to 20 pixels per thread.
+#ifdef CSPN_DEV_SINGLE
+// developer build for offline SASS studies (tools/sass_excerpt.py on a 10-second compile): only the headline kernels
+const std::vector<KernelCfg>& configs() {
+    static const std::vector<KernelCfg> v = [] {
+        KernelCfg k{5, 4, 8, {{nullptr, nullptr}, {nullptr, nullptr}}, {nullptr, nullptr}, {nullptr, nullptr}, {{nullptr, nullptr}, {nullptr, nullptr}},
+                    Cfg<5, 4, 8>::kSmemBytes, Cfg<5, 4, 8>::kSmemBytesChain};
+        k.fn[0][0] = (const void*)&cspn2d_cluster_kernel<5, 4, 8, false, false>;
+        k.fn_chain[0][0] = (const void*)&cspn2d_cluster_kernel<5, 4, 8, false, false, kForward, true>;
+        return std::vector<KernelCfg>{k};
+    }();
+    return v;
+}
+#else
 const std::vector<KernelCfg>& configs() {
     static const std::vector<KernelCfg> v = {
         make_cfg_chain<5, 4, 8>(),   // 40 rows x 128 cols, 20 px/thread
@@ -1158,6 +1219,7 @@ const std::vector<KernelCfg>& configs() {
     };
     return v;
 }
+#endif
 
 // One pass = one launch that advances every image by `iters` steps.
 struct PassPlan {
@@ -1605,6 +1667,18 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     prm.n_bands = pp.n_bands;
     prm.trace = g_trace;
     prm.hist = cb.hist; prm.flags = cb.flags; prm.chain_lane = pp.chain_lane;
+    {
+        // group size: at least 1.5 x the co-resident clusters, the groups as equal as possible.  Measured on cfg2-shaped batches
+        // (profiles/r02_tuning_log.md): a strip's left neighbour only 16 tasks back (15 clusters) is not always finished when
+        // its flag is looked at (+4.6 %), 24 back it is, and the shared columns then come from L2 (-2 % against one group,
+        // DRAM reads 1.25 x -> 1.0 x algorithmic).  CSPN_B200_CHAIN_GROUP overrides (0 = one group).
+        const long nq_all = (long)p.B * p.C * pp.n_bands;
+        long min_g = pp.max_clusters + (pp.max_clusters + 1) / 2;
+        if (const char* e = getenv("CSPN_B200_CHAIN_GROUP")) min_g = atol(e) > 0 ? atol(e) : nq_all;
+        long n_groups = min_g > 0 ? nq_all / min_g : 1;
+        if (n_groups < 1) n_groups = 1;
+        prm.chain_group = (int)(nq_all / n_groups);
+    }
     prm.n_peer = sc.n_peer;
     for (int i = 0; i < 7; ++i) prm.out_peer[i] = i < sc.n_peer ? sc.peer[i] : nullptr;
     prm.out_mc = sc.mc;
@@ -1637,9 +1711,14 @@ int launch_pass(const Problem2D& p, const PassPlan& pp, const void* fn, const fl
     if (chained) {
         // a task spins on the flag of its left neighbour strip, which another cluster sets: every cluster of the grid must be
         // resident (the grid is sized by the occupancy query; a cooperative launch makes that a guarantee, not a hope)
-        at[1].id = cudaLaunchAttributeCooperative;
-        at[1].val.cooperative = 1;
-        cfg.numAttrs = 2;
+        // (developer hook CSPN_B200_COOP=0: plain launch, for Nsight Compute -- its replay of a cooperative launch drops
+        // the cluster dimension; under the profiler kernels run alone, so residency holds anyway)
+        const char* coop = getenv("CSPN_B200_COOP");
+        if (!(coop && coop[0] == '0')) {
+            at[1].id = cudaLaunchAttributeCooperative;
+            at[1].val.cooperative = 1;
+            cfg.numAttrs = 2;
+        }
         CSPN_CUDA_TRY(cudaMemsetAsync(cb.flags, 0, cb.flag_bytes, stream));
     }
     void* args[4] = {(void*)&tm, (void*)&tm_blur, (void*)&tm_sparse, (void*)&prm};
@@ -1691,6 +1770,19 @@ int cluster2d_forward(const Problem2D& p, void* ws, size_t ws_bytes, cudaStream_
         const KernelCfg& kc = configs()[pp.cfg];
         rc = launch_pass(p, pp, (pp.chained ? kc.fn_chain : kc.fn)[general ? 1 : 0][p.norm_abs ? 1 : 0], p.blur, prev, dst, nullptr, 0, stream, sc,
                          pp.chained ? cb : ChainBuf());
+        if (rc != CSPN_OK && pp.chained && ip == 0) {
+            // the cooperative launch was refused (the grid cannot be made resident as a whole: SM partitioning, MPS limits, ...):
+            // nothing has run yet, so take the unchained plan, which needs no residency guarantee
+            cudaGetLastError();
+            clear_error();
+            rc = plan_for_launch(p, plan);
+            if (rc != CSPN_OK) return rc;
+            if (plan.n_pass > 1 && (!ws || ws_bytes < d_bytes)) { set_error("workspace too small for the unchained plan"); return CSPN_ERR_WORKSPACE; }
+            cb = ChainBuf();
+            ip = -1;
+            prev = nullptr;
+            continue;
+        }
         if (rc != CSPN_OK) return rc;
         ++*launches;
         prev = dst;

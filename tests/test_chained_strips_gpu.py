@@ -104,3 +104,18 @@ def test_chained_call_is_repeatable_and_graph_capturable():
             assert torch.equal(res, first)
     finally:
         os.environ.pop('CSPN_B200_CHAIN', None)
+
+
+@pytest.mark.parametrize('group', [1, 2, 3])
+def test_task_groups_do_not_change_the_result(group):
+    """CSPN_B200_CHAIN_GROUP: tasks run group by group (strip-major inside a group of image-channels; the last group takes the
+    remainder), which only reorders them."""
+    g, d, s = [t.cuda() for t in make_inputs(11, 7, 1, 48, 400)]
+    plain, _ = run(g, d, s, 9, '8sum', chain=False)
+    os.environ['CSPN_B200_CHAIN_GROUP'] = str(group)
+    try:
+        chained, plan = run(g, d, s, 9, '8sum', chain=True)
+    finally:
+        os.environ.pop('CSPN_B200_CHAIN_GROUP', None)
+    assert 'chained' in plan
+    assert torch.equal(chained, plain) if patch_of(plan) == patch_of(_) else torch.allclose(chained, plain, rtol=2e-6, atol=2e-6)
