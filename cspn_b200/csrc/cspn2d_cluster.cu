@@ -152,6 +152,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// shared-memory accesses by 32-bit shared address (the chained-strip history: a generic pointer that varies per step makes
+// ptxas rebuild the shared-window arithmetic at every access)
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // pull one box of a tensor into L2 (no shared-memory destination, no barrier): one instruction for a whole tile
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
@@ -262,13 +275,14 @@ struct Xch {
     uint32_t dn_data, dn_bar;   // CTA below: its slot 0 ("halo from above"), its full[0]
     bool has_up, has_dn;
     // warp roles as predicates for the branch-free publish: remote_up = this warp owns the CTA's top row and a CTA
-    // above exists; remote_dn likewise; sig_tx / sig = lane 0 arrives (with / without arming the tx count)
-    bool remote_up, remote_dn, sig_tx, sig;
+    // above exists; remote_dn likewise
+    bool remote_up, remote_dn;
+    uint32_t my_tx;       // tx bytes this warp's lane-0 arrival arms: rx_bytes in the CTA's first warp, 0 elsewhere
     bool first_lane, last_lane;
     const float* cbuf;    // this thread's first pixel of c' (row r is r*TW floats further)
     // chained strips (CHAIN kernels; set per task)
     bool store_hist;      // this lane owns the recorded column and the strip has a right neighbour strip
-    float* hin;           // this warp's 8 floats of step 0 in the history-in buffer; history-out lies kHistBytes further
+    uint32_t hin;         // shared address of this warp's 8 floats of step 0 in the history-in buffer; history-out lies kHistBytes further
 };
 
 // Publish the boundary rows of the new d into exchange buffer PAR (local shared memory, and the neighbour CTAs'
@@ -286,8 +300,9 @@ __device__ __forceinline__ void publish(const Xch& x, int wy, const float (&top)
     if (x.remote_up) store_row_remote(x.up_data + PAR * (uint32_t)K::kXchParityBytes, top, x.up_bar + 8 * PAR);
     if (x.remote_dn) store_row_remote(x.dn_data + PAR * (uint32_t)K::kXchParityBytes, bot, x.dn_bar + 8 * PAR);
     __syncwarp();
-    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
-    mbar_arrive_if(bar, x.sig);
+    // one arrival per warp (lane 0); the first warp's also arms the bytes the neighbour CTAs will deliver (expect_tx of 0
+    // bytes is a plain arrival): one predicated instruction and one predicate instead of two of each
+    mbar_arrive_expect_tx_if(bar, x.my_tx, x.first_lane);
 }
 
 // ---- one propagation step ---------------------------------------------------------------------------------------
@@ -343,7 +358,7 @@ __device__ __forceinline__ void row_edges_raw(const float (&v)[PC], float (&ed)[
 template <int PR, int PC, int NW, int PAR, bool PUBLISH, bool CHAIN = false>
 __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                          float (&din)[PR][PC], const float (&ein)[PR][2], float (&dout)[PR][PC],
-                                         float (&eout)[PR][2], float* hrow = nullptr) {
+                                         float (&eout)[PR][2], uint32_t hrow = 0) {
     using K = Cfg<PR, PC, NW>;
     const bool ul = CHAIN ? true : !x.first_lane, ur = !x.last_lane;
     // ---- A: own-row taps of the two boundary rows ----------------------------------------------------------------
@@ -365,14 +380,13 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
         load_row_smem(pu, u);
         load_row_smem(pd, d);
         if constexpr (CHAIN) {
-            ue[0] = *(x.first_lane ? hrow + 4 : pu - 1);
-            de[0] = *(x.first_lane ? hrow + 5 : pd - 1);
+            ue[0] = lds_f32(x.first_lane ? hrow + 16 : smem_u32(pu - 1));
+            de[0] = lds_f32(x.first_lane ? hrow + 20 : smem_u32(pd - 1));
             if (x.store_hist) {
-                float* q = hrow + K::kHistBytes / sizeof(float);      // history-out
-                *reinterpret_cast<float4*>(q) = make_float4(din[0][PC - 1], din[1][PC - 1], din[PR > 2 ? 2 : 0][PC - 1], din[PR > 3 ? 3 : 0][PC - 1]);
-                q[4] = u[PC - 1];
-                q[5] = d[PC - 1];
-                if constexpr (PR > 4) q[6] = din[PR > 4 ? 4 : 0][PC - 1];
+                const uint32_t q = hrow + (uint32_t)K::kHistBytes;      // history-out
+                sts_v4(q, make_float4(din[0][PC - 1], din[1][PC - 1], din[PR > 2 ? 2 : 0][PC - 1], din[PR > 3 ? 3 : 0][PC - 1]));
+                sts_v2(q + 16, u[PC - 1], d[PC - 1]);
+                if constexpr (PR > 4) sts_f32(q + 24, din[PR > 4 ? 4 : 0][PC - 1]);
             }
         } else {
             ue[0] = pu[-1];                               // pad floats are zero at the tile edges
@@ -436,13 +450,13 @@ __device__ __forceinline__ void iterate3(const Xch& x, int wy, uint32_t phase, c
     }
 #endif
     if constexpr (CHAIN && PUBLISH) {   // column -1 of my rows at the next step (row t+1 of the history)
-        const float* hn = hrow + K::kHistRow;
-        const float4 h = *reinterpret_cast<const float4*>(hn);
+        const uint32_t hn = hrow + K::kHistRow * 4;
+        const float4 h = lds_v4(hn);
         eout[0][0] = x.first_lane ? h.x : eout[0][0];
         eout[1][0] = x.first_lane ? h.y : eout[1][0];
         if constexpr (PR > 2) eout[2][0] = x.first_lane ? h.z : eout[2][0];
         if constexpr (PR > 3) eout[3][0] = x.first_lane ? h.w : eout[3][0];
-        if constexpr (PR > 4) eout[4][0] = x.first_lane ? hn[6] : eout[4][0];
+        if constexpr (PR > 4) eout[4][0] = x.first_lane ? lds_f32(hn + 24) : eout[4][0];
         static_assert(PR <= 5, "a history row has room for five patch rows");
     }
     if constexpr (PUBLISH) {   // seeds of the next step's boundary rows, into the now dead input set
@@ -516,8 +530,9 @@ __device__ __forceinline__ void publish_p(const Xch& x, int wy, const P2 (&top)[
         asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(
                          x.dn_data + PAR * (uint32_t)K::kXchParityBytes), "l"(bot[0]), "l"(bot[1]), "r"(x.dn_bar + 8 * PAR) : "memory");
     __syncwarp();
-    mbar_arrive_expect_tx_if(bar, x.rx_bytes, x.sig_tx);
-    mbar_arrive_if(bar, x.sig);
+    // one arrival per warp (lane 0); the first warp's also arms the bytes the neighbour CTAs will deliver (expect_tx of 0
+    // bytes is a plain arrival): one predicated instruction and one predicate instead of two of each
+    mbar_arrive_expect_tx_if(bar, x.my_tx, x.first_lane);
 }
 
 // Same phases as iterate3: A own-row taps of the boundary rows, B wait -> halo taps -> publish, C interior rows (seeded
@@ -577,7 +592,7 @@ __device__ __forceinline__ void iterate_p(Xch& x, int wy, uint32_t phase, const 
 template <int PR, int PC, int NW, int PAR, bool PUBLISH, bool CHAIN = false>
 __device__ __forceinline__ void step_fwd(Xch& x, int wy, uint32_t phase, const float (&w)[PR][PC][8],
                                          float (&din)[PR][PC], float (&ein)[PR][2], float (&dout)[PR][PC],
-                                         float (&eout)[PR][2], float* hrow = nullptr) {
+                                         float (&eout)[PR][2], uint32_t hrow = 0) {
     iterate3<PR, PC, NW, PAR, PUBLISH, CHAIN>(x, wy, phase, w, din, ein, dout, eout, hrow);
 #ifdef CSPN_TRACE
     ++x.step;
@@ -710,13 +725,12 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
     xc.rx_bytes = (uint32_t)((xc.has_up ? 1 : 0) + (xc.has_dn ? 1 : 0)) * TW * sizeof(float);
     xc.remote_up = xc.has_up && wy == 0;
     xc.remote_dn = xc.has_dn && wy == NW - 1;
-    xc.sig_tx = lane == 0 && wy == 0 && xc.rx_bytes != 0;
-    xc.sig = lane == 0 && !(wy == 0 && xc.rx_bytes != 0);
+    xc.my_tx = wy == 0 ? xc.rx_bytes : 0u;
     xc.first_lane = lane == 0;
     xc.last_lane = lane == 31;
     xc.cbuf = cbuf + (size_t)(wy * PR) * TW + lane * PC;
-    xc.store_hist = false; xc.hin = nullptr;
-    if constexpr (CHAIN) xc.hin = hist_in + wy * 8;
+    xc.store_hist = false; xc.hin = 0;
+    if constexpr (CHAIN) xc.hin = smem_u32(hist_in + wy * 8);
 
     // Persistent clusters: cluster q runs tasks q, q + Q, q + 2Q, ...  (task = (image*C + channel, strip))
     const int n_tasks = prm.n_tasks;
@@ -1078,28 +1092,28 @@ cspn2d_cluster_kernel(const __grid_constant__ CUtensorMap tm_guidance, const __g
         for (int r = 0; r < PR; ++r) row_edges_raw<PC>(d[r], e[r]);
         if constexpr (CHAIN) {          // column -1 of lane 0's rows at step 0 (row 0 of the history)
 #pragma unroll
-            for (int r = 0; r < PR; ++r) e[r][0] = xc.first_lane ? xc.hin[r < 4 ? r : 6] : e[r][0];
+            for (int r = 0; r < PR; ++r) e[r][0] = xc.first_lane ? lds_f32(xc.hin + 4 * (r < 4 ? r : 6)) : e[r][0];
         }
         float d2[PR][PC], e2[PR][2];    // second register set: (d,e) -> (d2,e2) on even steps, back on odd ones
 #pragma unroll
         for (int r = 0; r < PR; ++r) load_row_smem(xc.cbuf + r * TW, d2[r]);   // accumulators of the first step start from c'
         int it = 0;
         for (; it + 2 < iters; it += 2) {   // steady state: every step publishes
-            step_fwd<PR, PC, NW, 0, true, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * K::kHistRow);
+            step_fwd<PR, PC, NW, 0, true, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * (K::kHistRow * 4));
             ph0 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d2);
-            step_fwd<PR, PC, NW, 1, true, CHAIN>(xc, wy, ph1, w, d2, e2, d, e, xc.hin + (it + 1) * K::kHistRow);
+            step_fwd<PR, PC, NW, 1, true, CHAIN>(xc, wy, ph1, w, d2, e2, d, e, xc.hin + (it + 1) * (K::kHistRow * 4));
             ph1 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d);
         }
         if (iters - it == 2) {              // the last step of a task has nobody to publish to
-            step_fwd<PR, PC, NW, 0, true, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * K::kHistRow);
+            step_fwd<PR, PC, NW, 0, true, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * (K::kHistRow * 4));
             ph0 ^= 1;
             if constexpr (MODE == kStoreSteps) store_step(d2);
-            step_fwd<PR, PC, NW, 1, false, CHAIN>(xc, wy, ph1, w, d2, e2, d, e, xc.hin + (it + 1) * K::kHistRow);
+            step_fwd<PR, PC, NW, 1, false, CHAIN>(xc, wy, ph1, w, d2, e2, d, e, xc.hin + (it + 1) * (K::kHistRow * 4));
             ph1 ^= 1;
         } else if (iters - it == 1) {
-            step_fwd<PR, PC, NW, 0, false, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * K::kHistRow);
+            step_fwd<PR, PC, NW, 0, false, CHAIN>(xc, wy, ph0, w, d, e, d2, e2, xc.hin + it * (K::kHistRow * 4));
             ph0 ^= 1;
         }
         CSPN_STAMP(xc, kTraceEvents - 2);
