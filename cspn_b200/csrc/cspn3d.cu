@@ -201,6 +201,111 @@ step3d_paddle_vec4_kernel(const float* __restrict__ g, const float* __restrict__
         make_float4(__fdiv_rn(acc[0], S[0]), __fdiv_rn(acc[1], S[1]), __fdiv_rn(acc[2], S[2]), __fdiv_rn(acc[3], S[3]));
 }
 
+// '26sum' / '26sum_abs' (gathered affinities + centre term, the cspn.py-style generalisation) straight from the RAW guidance,
+// like the 'paddle' kernel above: a_k(p) = g_k(p + off_k) (zero outside the volume) is read where it lies -- an aligned float4
+// of the shifted row plus, for dx = +-1, one neighbouring scalar (an L1 hit: the next thread's quad) -- S = sum |a_k|,
+// w_k = a_k * (1 / S) (one division per voxel; where 1 / S overflows, i.e. S subnormal, the quotients are formed exactly),
+// kappa = 1 - sum_k w_k from the products as the weight-plane path forms it from its quotients, out = kappa d0 + sum_k w_k
+// cur(p + off_k).  No prep launch, no 27-plane workspace (1.65 GB for cfg4), 26 + 2 instead of 29 + 27/N planes per step.
+#ifndef CSPN3D_GATHER_BLOCKS
+#define CSPN3D_GATHER_BLOCKS 3
+#endif
+template <bool ABS>
+__global__ void __launch_bounds__(128, CSPN3D_GATHER_BLOCKS)
+step3d_gather_vec4_kernel(const float* __restrict__ g, const float* __restrict__ d0, const float* __restrict__ cur,
+                          float* __restrict__ dst, int C, int D, int H, int W) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z % D, c = blockIdx.z / D;   // c = volume * C + channel
+    // no early exit: the x-neighbours of a shifted quad come from the neighbouring lanes (a warp is 32 consecutive quads of
+    // one row), so every lane takes part in the shuffles; lanes outside the volume contribute the zero padding
+    const bool active = x < W && y < H;
+    const int lane = threadIdx.x;
+    const size_t HW = (size_t)H * W, V = (size_t)D * HW;
+    const size_t p = (size_t)z * HW + (size_t)y * W + x;
+    g += (size_t)(c / C) * 26 * V;
+    const float* cc = cur + (size_t)c * V;
+    // all loads first, back to back (the kernel lives on loads in flight); the lane shuffles that complete the shifted quads after
+    float4 a[26];
+    float edge[26];
+#pragma unroll
+    for (int k = 0; k < 26; ++k) {
+        const int zz = z + off3_dz(k), yy = y + off3_dy(k);
+        const bool in = active && zz >= 0 && zz < D && yy >= 0 && yy < H;
+        const float* src = g + k * V + (size_t)zz * HW + (size_t)yy * W + x;
+        a[k] = in ? ld_stream(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        edge[k] = 0.f;
+        if (off3_dx(k) == 1 && lane == 31 && in && x + 4 < W) edge[k] = __ldg(src + 4);    // the warp's edge lanes: one scalar each
+        if (off3_dx(k) == -1 && lane == 0 && in && x > 0) edge[k] = __ldg(src - 1);
+    }
+    float S[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 26; ++k) {
+        const float4 q = a[k];
+        float4 v = q;
+        if (off3_dx(k) == 1) {           // elements x+1 .. x+4: the last one is the next lane's first
+            const float e = __shfl_down_sync(0xffffffffu, q.x, 1);
+            v = make_float4(q.y, q.z, q.w, lane == 31 ? edge[k] : e);
+        } else if (off3_dx(k) == -1) {   // elements x-1 .. x+2
+            const float e = __shfl_up_sync(0xffffffffu, q.w, 1);
+            v = make_float4(lane == 0 ? edge[k] : e, q.x, q.y, q.z);
+        }
+        if (ABS) v = make_float4(fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w));
+        a[k] = v;
+        S[0] += fabsf(v.x); S[1] += fabsf(v.y); S[2] += fabsf(v.z); S[3] += fabsf(v.w);
+    }
+    if (!active) return;
+    float rows[3][3][6];
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int zz = z + dz, yy = y + dy;
+            float* r = rows[dz + 1][dy + 1];
+            if (zz >= 0 && zz < D && yy >= 0 && yy < H) {
+                const float* src = cc + (size_t)zz * HW + (size_t)yy * W + x;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w;
+                r[0] = x > 0 ? __ldg(src - 1) : 0.f;
+                r[5] = x + 4 < W ? __ldg(src + 4) : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) r[i] = 0.f;
+            }
+        }
+    const float inv[4] = {__fdiv_rn(1.f, S[0]), __fdiv_rn(1.f, S[1]), __fdiv_rn(1.f, S[2]), __fdiv_rn(1.f, S[3])};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 26; ++k) {
+        const float* r = rows[off3_dz(k) + 1][off3_dy(k) + 1];
+        const int o = 1 + off3_dx(k);
+        const float w0 = a[k].x * inv[0], w1 = a[k].y * inv[1], w2 = a[k].z * inv[2], w3 = a[k].w * inv[3];
+        s[0] += w0; s[1] += w1; s[2] += w2; s[3] += w3;
+        acc[0] = fmaf(w0, r[o], acc[0]);
+        acc[1] = fmaf(w1, r[o + 1], acc[1]);
+        acc[2] = fmaf(w2, r[o + 2], acc[2]);
+        acc[3] = fmaf(w3, r[o + 3], acc[3]);
+    }
+    if (inv[0] > 8.0e37f || inv[1] > 8.0e37f || inv[2] > 8.0e37f || inv[3] > 8.0e37f) {   // cold: S subnormal, 1 / S overflowed
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!(inv[j] > 8.0e37f)) continue;
+            acc[j] = 0.f; s[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 26; ++k) {
+                const float av = j == 0 ? a[k].x : (j == 1 ? a[k].y : (j == 2 ? a[k].z : a[k].w));
+                const float w = __fdiv_rn(av, S[j]);
+                s[j] += w;
+                acc[j] = fmaf(w, rows[off3_dz(k) + 1][off3_dy(k) + 1][1 + off3_dx(k) + j], acc[j]);
+            }
+        }
+    }
+    const float4 dz0 = __ldg(reinterpret_cast<const float4*>(d0 + (size_t)c * V + p));
+    *reinterpret_cast<float4*>(dst + (size_t)c * V + p) =
+        make_float4(fmaf(1.f - s[0], dz0.x, acc[0]), fmaf(1.f - s[1], dz0.y, acc[1]), fmaf(1.f - s[2], dz0.z, acc[2]),
+                    fmaf(1.f - s[3], dz0.w, acc[3]));
+}
+
 }  // namespace
 
 // Volumes per launch group: as many as keep the group's workspace under kMaxWorkspace3d (and gridDim.z legal).
@@ -244,15 +349,18 @@ int generic3d_forward(const float* guidance, const float* feat, float* out, int 
     const bool vec4_all = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out) |
                                               reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(guidance)) % 16 == 0);
     const char* raw_env = getenv("CSPN_B200_3D_PADDLE");     // developer hook: "planes" forces the prep + weight-plane path
-    if (mode == 2 && vec4_all && !(raw_env && raw_env[0] == 'p') && (size_t)D * C * B <= 65535 &&
+    if (vec4_all && !(raw_env && raw_env[0] == 'p') && (size_t)D * C * B <= 65535 &&
         (iters == 1 || ws_bytes >= (size_t)B * C * V * sizeof(float))) {
-        // 'paddle': gates straight from the raw guidance, every volume in one launch per step; the workspace's first
-        // C*B*V floats are the ping-pong buffer
+        // gates straight from the raw guidance ('paddle': own location; '26sum[_abs]': gathered), every volume in one launch
+        // per step; the workspace's first C*B*V floats are the ping-pong buffer
         float* tmp = static_cast<float*>(ws);
         const float* cur = feat;
         float* dst = (iters & 1) ? out : tmp;
+        const dim3 grid((W / 4 + 31) / 32, (H + 3) / 4, D * C * B), block(32, 4);
         for (int it = 0; it < iters; ++it) {
-            step3d_paddle_vec4_kernel<<<dim3((W / 4 + 31) / 32, (H + 3) / 4, D * C * B), dim3(32, 4), 0, stream>>>(guidance, cur, dst, C, D, H, W);
+            if (mode == 2) step3d_paddle_vec4_kernel<<<grid, block, 0, stream>>>(guidance, cur, dst, C, D, H, W);
+            else if (mode == 1) step3d_gather_vec4_kernel<true><<<grid, block, 0, stream>>>(guidance, feat, cur, dst, C, D, H, W);
+            else step3d_gather_vec4_kernel<false><<<grid, block, 0, stream>>>(guidance, feat, cur, dst, C, D, H, W);
             ++*launches;
             cur = dst;
             dst = (dst == out) ? tmp : out;

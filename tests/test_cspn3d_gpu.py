@@ -46,6 +46,7 @@ def test_3d_full_size_properties():
 @pytest.mark.parametrize('cap_kb,launches', [(None, 1 + 4), (300, 2 * (1 + 4)), (100, 3 * (1 + 4))])
 def test_3d_volume_groups_including_a_ragged_last_group(cap_kb, launches, monkeypatch):
     """One launch covers a group of volumes; the workspace cap decides the group size (3 volumes: 3, 2+1, 1+1+1)."""
+    monkeypatch.setenv('CSPN_B200_3D_PADDLE', 'planes')              # the prep + weight-plane path (W % 4 != 0 fallback) is the one with groups
     if cap_kb:
         monkeypatch.setenv('CSPN_B200_MAX_WS3D_KB', str(cap_kb))     # one volume needs 29 * 6*10*16 * 4 B = 111 KB
     g, f = make_inputs_3d(4, 3, 2, 6, 10, 16)
@@ -113,3 +114,34 @@ def test_3d_per_channel_gates_like_demo_py(mode):
         gg[:, 26 * c:26 * (c + 1)] = g1.grad.cpu()
         gf[:, c:c + 1] = f1.grad.cpu()
     assert torch.allclose(gc.grad.cpu(), gg, rtol=1e-5, atol=1e-7) and torch.allclose(fc.grad.cpu(), gf, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('mode', ['26sum', '26sum_abs', 'paddle'])
+def test_3d_direct_path_agrees_with_the_weight_plane_path(mode, monkeypatch):
+    """W % 4 == 0: gates straight from the raw guidance, one launch per step, no weight planes; CSPN_B200_3D_PADDLE=planes
+    forces prep + 27 weight planes (the path odd widths take).  Same arithmetic up to one rounding per weight."""
+    g, f = [t.cuda() for t in make_inputs_3d(9, 2, 2, 7, 11, 24, signed=(mode == '26sum'))]
+    direct = cspn_b200.propagate3d(g, f, 6, mode)
+    torch.cuda.synchronize()
+    assert _lib.lib().cspn_last_launches() == 6
+    monkeypatch.setenv('CSPN_B200_3D_PADDLE', 'planes')
+    planes = cspn_b200.propagate3d(g, f, 6, mode)
+    torch.cuda.synchronize()
+    assert _lib.lib().cspn_last_launches() == 7
+    ok, ratio, normwise = onp.parity_ok(direct.cpu().numpy(), planes.cpu().numpy(), 1e-5)
+    assert ok, (ratio, normwise)
+
+
+def test_3d_degenerate_gates_follow_ieee_division():
+    """A voxel whose gates are all zero (own location for 'paddle', the 26 gathered taps for '26sum_abs'): 0 / 0 = NaN, and the
+    NaN front then moves one voxel per step -- on the direct path exactly as in the oracle."""
+    g, f = make_inputs_3d(3, 1, 1, 6, 8, 12)
+    g[:, :, 1:4, 2:5, 3:6] = 0.0
+    for mode in ('26sum_abs', 'paddle'):
+        for n in (1, 2):
+            ref = c_oracle.cspn3d(g.numpy(), f.numpy(), n, mode)
+            out = cspn_b200.propagate3d(g.cuda(), f.cuda(), n, mode).cpu().numpy()
+            assert np.isnan(ref).any()
+            assert np.array_equal(np.isnan(out), np.isnan(ref)), (mode, n)
+            ok, ratio, normwise = onp.parity_ok(out, ref, 1e-4)
+            assert ok, (mode, n, ratio, normwise)
